@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- voxel-steps/s of the full smoke step (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C2|C3|C1|NxNxN]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one full simulation tick (source/mask fill, forcing, clamp, 30 x 2 red-black SOR half-sweeps,
+u/v/w advection, density advection) on synthetic plume scenes (no RNG: fields start at
+zero, sources/obstacles are analytic spheres).  N = 1 runs configs[1] (256^3 rising plume) with the
+reference's own solver schedule (RBGS, omega 1.9, 30 iterations -- the only schedule that has a reference
+to be identical to; BASELINE's "40 Jacobi iterations" has no counterpart in the reference, SURVEY.md point 1).
+
+One JSON line on stdout (rank 0):
+  value     whole-job voxel-steps/s, fields resident in HBM, no host traffic in the timed region
+  e2e       the same through the reference-facing call (simulate(): smk_step with a HOST density buffer,
+            the device->host copy of every step inside the timed region)
+  roofline  the dominant kernel (pressure half-sweep): algorithmic bytes per launch / its mean duration
+            (CUDA events recorded by the library on its stream during the timed region) / measured HBM peak
+  cpu_baseline   the reference's kernel bodies as an OpenMP host loop (oracle/_ref/libref_cpu.so; "port" =
+            oracle/liboracle.so if the former is absent) on a bounded sample, rank 0, N = 1 only
+--impl reference times that CPU implementation alone (all host threads) and prints the same line.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "voxel_steps_per_sec"
+UNIT = "voxel-steps/s"
+BYTES_PER_CELL_HALFSWEEP = 25  # u,v,w read+write (24 B) + 1 B mask information per cell
+
+
+def parse_workload(name, gpus):
+    import pyoracle as po
+    if name is None:
+        name = "C2"
+    if name in po.SCENES:
+        sc = po.SCENES[name]
+        label = {"C1": "C1 80^3 default scene (source r5 + solid sphere r13)",
+                 "C2": "C2 256^3 open-boundary rising plume (source (128,32,128) r16, alpha 15)",
+                 "C3": "C3 512^3 plume with solid-sphere obstacle",
+                 "C4": "C4 1024^3 inverted-gravity plume"}[name]
+        return name, sc, label
+    dims = [int(v) for v in name.lower().split("x")]
+    W, H, D = dims if len(dims) == 3 else (dims[0],) * 3
+    sc = (W, H, D, -9.82, 15.0, [(W / 2, H / 8, D / 2, max(2.0, W / 16))], [])
+    return name, sc, f"{W}x{H}x{D} rising plume"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML, 100 ms)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {}
+        for n in dir(nv):
+            if n.startswith("nvmlClocksEventReason") or n.startswith("nvmlClocksThrottleReason"):
+                v = getattr(nv, n)
+                if isinstance(v, int) and v and (v & (v - 1)) == 0:
+                    names[v] = n.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", "")
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, n in names.items():
+                    if r & bit and "None" not in n and "GpuIdle" not in n:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_engine():
+    """The reference's own CPU implementation of the path (preferred) or the oracle port."""
+    import pyoracle as po
+    if po.have_ref_cpu():
+        return po.RefCPU, "reference", po
+    return (lambda W, H, D: po.Oracle(W, H, D, contract=0)), "port", po
+
+
+def time_cpu(scene, budget_s, steps=None, warmup=0):
+    """Time the CPU implementation on a bounded sample of `scene`: full x,y extent, the first Ds cell planes
+    (Ds halved until the estimated run fits `budget_s`).  Returns (voxel-steps/s, cores, kind, sample, ms_per_step)."""
+    eng, kind, po = cpu_engine()
+    W, H, D = scene[:3]
+    cores = os.cpu_count() or 1
+    if kind == "reference":
+        po.RefCPU.set_threads(cores)
+    else:
+        po.Oracle.set_threads(cores)
+    # probe on a thin slab to estimate the cost per voxel-step
+    Dp = min(D, 16)
+    sub = (W, H, Dp) + tuple(scene[3:])
+    e = eng(W, H, Dp); po.setup_scene(e, sub)
+    e.step(0.01)
+    t0 = time.perf_counter(); e.step(0.05); est = (time.perf_counter() - t0) / (W * H * Dp)
+    if hasattr(e, "close"):
+        e.close()
+    n_steps = (steps or 0) + warmup
+    Ds = D
+    if steps is None:  # choose the number of ticks for ~budget on the full volume, else shrink the volume
+        while Ds > 16 and est * W * H * Ds * 2 > budget_s:
+            Ds //= 2
+        steps = max(1, min(20, int(budget_s / (est * W * H * Ds)) - 1))
+        warmup = 1
+    else:
+        while Ds > 16 and est * W * H * Ds * n_steps > budget_s:
+            Ds //= 2
+    sub = (W, H, Ds) + tuple(scene[3:])
+    e = eng(W, H, Ds); po.setup_scene(e, sub)
+    for t in range(warmup):
+        e.step(po.tick_dt(t))
+    t0 = time.perf_counter()
+    for t in range(steps):
+        e.step(po.tick_dt(t + warmup))
+    dt = time.perf_counter() - t0
+    if hasattr(e, "close"):
+        e.close()
+    sample = (f"{steps} ticks of {W}x{H}x{Ds}" + ("" if Ds == D else f" (first {Ds} of {D} z-planes of the workload)")
+              + f", {cores} OpenMP threads")
+    return W * H * Ds * steps / dt, cores, kind, sample, dt / steps * 1e3
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    wname, scene, label = parse_workload(args.workload, args.gpus)
+    val, cores, kind, sample, ms = time_cpu(scene, budget_s=150.0, steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": label + "; reference schedule RBGS omega=1.9 x30; CPU implementation of the reference step",
+                   "solver": "rbgs", "iterations": 30},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None, help="C1|C2|C3|C4 or NxNxN (default: C2 at N=1)")
+    ap.add_argument("--fuse", type=int, default=0, help="half-sweeps fused per pressure launch (0 = library default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import pyoracle as po
+    import smoke_simulation_b200 as smk
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the smoke step has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world > 1:
+        raise SystemExit("bench.py: multi-GPU z-slab run not wired yet in this revision")
+
+    wname, scene, label = parse_workload(args.workload, args.gpus)
+    W, H, D = scene[:3]
+    sim = smk.SmokeSim(W, H, D)
+    po.setup_scene(sim, scene)
+    sim.set_solver(0, 30, args.fuse)
+    stream = torch.cuda.current_stream()
+    sim.set_stream(stream.cuda_stream)
+    host = torch.empty((D, H, W), dtype=torch.float32, pin_memory=True)
+    host_ptr = host.data_ptr()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, Wm = args.steps, args.warmup
+    tick = 0
+    for _ in range(Wm):
+        sim.step_async(po.tick_dt(tick)); tick += 1
+    sim.sync()
+
+    # ---- timed region 1: device-resident throughput ("value") ------------------------------------------------
+    sim.reset_timers()
+    l0 = sim.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        e0.record(stream)
+        for _ in range(K):
+            sim.step_async(po.tick_dt(tick)); tick += 1
+        e1.record(stream)
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = sim.launch_count() - l0
+    times = sim.stage_times()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    value = W * H * D * K * world / (ms * 1e-3)
+
+    # ---- timed region 2: end to end through the reference-facing call (host buffer, D2H every step) --------
+    for _ in range(min(Wm, 2)):
+        sim.step_ptr(po.tick_dt(tick), host_ptr); tick += 1
+    barrier()
+    w0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(K):
+        sim.step_ptr(po.tick_dt(tick), host_ptr); tick += 1   # blocking, like simulate() (cu:814)
+    e1.record(stream)
+    barrier()
+    ms_e2e = max(e0.elapsed_time(e1), 0.0)
+    wall_e2e = (time.perf_counter() - w0) * 1e3
+    ms_e2e = max(ms_e2e, wall_e2e)  # the call is blocking: host time is part of the user-visible cost
+    if world > 1:
+        t = torch.tensor([ms_e2e], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms_e2e = float(t.item())
+    e2e = W * H * D * K * world / (ms_e2e * 1e-3)
+    checksum = float(host.sum())
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        p_ms, p_launches = times["pressure"]
+        per_launch_ms = p_ms / max(p_launches, 1)
+        cells = W * H * D
+        alg_bytes = BYTES_PER_CELL_HALFSWEEP * cells
+        halfsweeps_per_launch = 60 * K / max(p_launches, 1)
+        achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+        roofline = {
+            "bound": "hbm", "kernel": "pressure half-sweep (red-black SOR on u,v,w)", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": per_launch_ms,
+            "halfsweeps_per_launch": halfsweeps_per_launch,
+            "reference_equivalent_GBps": achieved * halfsweeps_per_launch,
+            "stage_ms_per_step": {k: v[0] / K for k, v in times.items()},
+        }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": label + "; reference schedule RBGS omega=1.9 x30", "grid": [W, H, D], "solver": "rbgs",
+                       "iterations": 30, "fuse": args.fuse, "parallelism": f"zslab{world}",
+                       "l2": f"state {(2 * cells * 4 + 6 * (W + 1) * (H + 1) * (D + 1) * 4 + 2 * cells) / 1e6:.0f} MB "
+                             "(> 126 MB L2 for every grid >= 160^3): inputs larger than L2, no explicit flush"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 544, "d2h_bytes_per_step": cells * 4,
+                    "ms_per_step": ms_e2e / K, "api": "smk_step(sim, dt, host_density) == simulate(smoke_grid, dt)",
+                    "note": "per-step inputs are the scene objects + dt/gravity/buoyancy, passed as kernel parameters",
+                    "density_checksum": checksum},
+            "gpu_launches": launches,
+            "clocks": clk.summary(),
+            "roofline": roofline,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            val, cores, kind, sample, _ = time_cpu(scene, budget_s=20.0)
+            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+        print(json.dumps(line), flush=True)
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

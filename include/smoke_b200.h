@@ -1,0 +1,164 @@
+/*
+ * smoke_b200.h -- C ABI of the B200-native smoke step (libsmoke_b200.so).
+ *
+ * This is the drop-in boundary underneath the reference's host entry points
+ * (reference: project/smokeSimulation.cuh:4-17).  Plain pointers and sizes only; no CUDA, torch
+ * or C++ types.  Every entry point names the reference interface it replaces (file:line under
+ * /root/reference, "cu" = project/smokeSimulation.cu).  The C++ wrappers with the reference's
+ * exact signatures live in smoke-simulation_b200/host/smokeSimulation.cuh + csrc/dropin.cu and are
+ * ~10-line forwards to these functions on one process-global handle.
+ *
+ * There is no CPU fallback: every compute entry point launches sm_100a kernels and returns
+ * SMK_ERR_CUDA if no usable device is present.
+ *
+ * Array layout at this boundary is the reference's: cell fields x + y*W + z*W*H,
+ * staggered fields x + y*(W+1) + z*(W+1)*(H+1), x fastest (cu:146-147).  Internally the
+ * staggered fields are stored with a padded row pitch; smk_get_field / smk_set_field convert.
+ */
+#ifndef SMOKE_B200_H
+#define SMOKE_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMK_ABI_VERSION 1
+
+typedef struct smk_sim smk_sim; /* opaque */
+
+/* status codes (the reference has none: it prints and exit(-1)s, cu:131-135; the .cuh wrappers keep
+ * that behaviour on top of these) */
+enum {
+    SMK_OK = 0,
+    SMK_ERR_CUDA = 1,      /* a CUDA runtime call failed; see smk_last_error()      */
+    SMK_ERR_ARG = 2,       /* bad argument (null handle, id out of range, ...)      */
+    SMK_ERR_LIMIT = 3,     /* more objects than SMK_MAX_OBJECTS                     */
+    SMK_ERR_REACH = 4,     /* slab mode: backtrace reach exceeded the ghost depth   */
+    SMK_ERR_TRANSPORT = 5  /* slab mode: halo transport missing or failed           */
+};
+
+/* field ids for smk_get_field / smk_set_field (same numbering as oracle/smoke_oracle.h) */
+enum { SMK_FIELD_SMOKE = 0, SMK_FIELD_U = 1, SMK_FIELD_V = 2, SMK_FIELD_W = 3, SMK_FIELD_MASK = 4 };
+/* buffer selectors: the reference ping-pongs two buffers per field (cu:16-24, 707-708) */
+enum { SMK_BUF_NOW = 0, SMK_BUF_PAST = 1, SMK_BUF_0 = 2, SMK_BUF_1 = 3 };
+
+/* pressure-solver variants.  Only RBGS is the reference's (cu:356-394, 797-801). */
+enum {
+    SMK_SOLVER_RBGS = 0,       /* red-black SOR on the face velocities, omega 1.9 -- reference parity */
+    SMK_SOLVER_JACOBI = 1      /* damped Jacobi on the same velocity form -- extension, no reference  */
+};
+
+/* stage ids for smk_stage_time() */
+enum {
+    SMK_STAGE_FILL = 0, SMK_STAGE_FORCE = 1, SMK_STAGE_PRESSURE = 2, SMK_STAGE_ADVECT_VEL = 3,
+    SMK_STAGE_ADVECT_SMOKE = 4, SMK_STAGE_READBACK = 5, SMK_STAGE_COUNT = 6
+};
+
+#define SMK_MAX_OBJECTS 16 /* per type; the reference's device arrays hold 3 (cu:56, 221-233) */
+
+/* ---- lifetime -------------------------------------------------------------------------------------- */
+
+/* replaces initializeVolume(float* smoke_grid, w, h, d)  (smokeSimulation.cuh:8, cu:124-238).
+ * smoke0_host: W*H*D floats or NULL (= zeros).  All second buffers are zero-initialised (the
+ * reference leaves them uninitialised).  Mask: fluid everywhere, solid on y == 0. */
+int smk_create(smk_sim** out, unsigned W, unsigned H, unsigned D, const float* smoke0_host);
+
+/* one z-slab of a W x H x D grid for multi-GPU runs (no reference counterpart).
+ * The slab owns cell planes [z_begin, z_end) and keeps `ghost` extra planes on each inner side. */
+int smk_create_slab(smk_sim** out, unsigned W, unsigned H, unsigned D, unsigned z_begin, unsigned z_end,
+                    unsigned ghost, const float* smoke0_host_full);
+
+/* replaces deleteVolume()  (smokeSimulation.cuh:9, cu:240-248) */
+int smk_destroy(smk_sim* s);
+
+/* replaces getGPUProperties()  (smokeSimulation.cuh:3, cu:62-85): prints the same property lines */
+int smk_print_gpu_properties(void);
+
+/* ---- scene and parameters -------------------------------------------------------------------------- */
+
+/* replace addObstacle / addSmokeSource / updateObjectPos  (smokeSimulation.cuh:12-14, cu:88-109).
+ * Return the new object's id (dense, creation order, shared between both types) or -SMK_ERR_*. */
+int smk_add_obstacle(smk_sim* s, float x, float y, float z, float vx, float vy, float vz, float r);
+int smk_add_source(smk_sim* s, float x, float y, float z, float r);
+int smk_update_object_pos(smk_sim* s, int id, float x, float y, float z);
+
+/* replace getGravity() / getBuoyancy()  (smokeSimulation.cuh:16-17, cu:31-36): stable pointers to
+ * library-owned floats that the caller may write between steps; re-read at every step. */
+float* smk_gravity_ptr(smk_sim* s);
+float* smk_buoyancy_ptr(smk_sim* s);
+
+/* solver selection (extension; defaults = the reference: RBGS, 30 iterations, cu:797).
+ * fuse = number of half-sweeps fused per kernel launch (temporal blocking); 0 = library default,
+ * 1 = one launch per half-sweep.  Results are identical for every fuse value. */
+int smk_set_solver(smk_sim* s, int variant, int iterations, int fuse);
+
+/* ---- the step ---------------------------------------------------------------------------------------- */
+
+/* replaces simulate(float* smoke_grid, float dt)  (smokeSimulation.cuh:5, cu:774-819).
+ * Runs flip, source/mask fill, forcing, clamp, the pressure sweeps, velocity and density advection.
+ * density_host: W*H*D floats that receive the new density (blocking, like cu:814), or NULL to skip
+ * the device->host round trip (the result stays on the device; smk_density_device()). */
+int smk_step(smk_sim* s, float dt, float* density_host);
+
+/* same, without waiting: returns after enqueueing; smk_sync() waits.  density_host may be NULL. */
+int smk_step_async(smk_sim* s, float dt, float* density_host);
+int smk_sync(smk_sim* s);
+
+/* device pointer to the density produced by the last step, reference layout (W*H*D floats).
+ * Replaces the D2H + glTexSubImage3D round trip of cu:814 / boundingBox.cpp:380-385. */
+const float* smk_density_device(smk_sim* s);
+
+/* run the whole step on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL = own stream */
+int smk_set_stream(smk_sim* s, void* cuda_stream);
+
+/* ---- stage-level entry points (per-kernel parity tests; same order as cu:777-810) ------------------- */
+int smk_stage_flip(smk_sim* s);                         /* cu:777-779 */
+int smk_stage_fill(smk_sim* s);                         /* cu:714-771 */
+int smk_stage_force_clamp(smk_sim* s, float dt);        /* cu:789 + cu:791 */
+int smk_stage_pressure_halfsweep(smk_sim* s, int offset); /* cu:799-800, one launch */
+int smk_stage_pressure(smk_sim* s);                     /* cu:797-801, all iterations, fused as configured */
+int smk_stage_advect_velocity(smk_sim* s, float dt);    /* cu:805-807 */
+int smk_stage_advect_smoke(smk_sim* s, float dt);       /* cu:810 */
+
+/* ---- field access (tests, checkpoints) --------------------------------------------------------------- */
+/* copy a whole field in the reference layout.  In slab mode only the planes this slab stores are
+ * touched (host arrays are still full-size). */
+int smk_get_field(smk_sim* s, int field, int which, void* host_dst);
+int smk_set_field(smk_sim* s, int field, int which, const void* host_src);
+int smk_index_now(smk_sim* s);
+
+/* max |div| over interior fluid cells of the "now" velocities (formula cu:379-381), by a device
+ * reduction (warp shuffles + one atomic per block).  The reference computes no residual. */
+int smk_max_divergence(smk_sim* s, float* out);
+
+/* ---- measurement -------------------------------------------------------------------------------------- */
+/* accumulated device time (CUDA events on the step's stream) and launch count per stage since the
+ * last smk_reset_timers().  Events are always recorded; reading them synchronises. */
+int smk_stage_time(smk_sim* s, int stage, double* ms_total, long* launches);
+int smk_reset_timers(smk_sim* s);
+/* kernels launched by this handle since creation */
+long smk_launch_count(smk_sim* s);
+
+/* ---- multi-GPU halo transport (slab mode) --------------------------------------------------------------- */
+/* Caller-provided exchange: called from smk_step when ghost planes of a field set must be refreshed.
+ * set: 0 = u,v,w "now", 1 = density "now".  For every listed region the callee must send `send_ptr`
+ * (device, contiguous, `bytes` long) to the neighbour on `side` (0 = lower z, 1 = upper z) and receive
+ * the neighbour's matching planes into `recv_ptr`.  All work must be ordered on `cuda_stream`. */
+typedef struct {
+    int side;       /* 0 = lower-z neighbour, 1 = upper-z neighbour */
+    void* send_ptr; /* my owned boundary planes */
+    void* recv_ptr; /* my ghost planes          */
+    size_t bytes;
+} smk_halo_region;
+typedef int (*smk_exchange_fn)(void* ctx, int set, const smk_halo_region* regions, int nregions, void* cuda_stream);
+int smk_set_exchange(smk_sim* s, smk_exchange_fn fn, void* ctx);
+
+const char* smk_last_error(smk_sim* s);
+int smk_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,35 @@
+// grid.h -- HBM data layout shared by the host code and the kernels.
+//
+// Cell fields (density, mask, stencil code): the reference layout, c = x + y*W + (z-zlo)*W*H.
+// Staggered fields (u, v, w): "node" layout with a padded row pitch so that every row starts on a
+// 32-byte sector and TMA / float4 access is legal: n = x + y*P + (z-zlo)*P*(H+1), P = roundup(W+1, 8).
+// Node (x,y,z) holds the three LOW faces of cell (x,y,z): u[x,y,z] between cells x-1|x, v between
+// y-1|y, w between z-1|z (MAC convention of the reference).  z is the slowest index, so a
+// z-slab [zlo, zlo+nz) of any field is one contiguous range (multi-GPU halos need no packing).
+#pragma once
+#include <cstdint>
+
+struct GridP {
+    int W, H, D;      // global cell counts
+    int P;            // node row pitch in floats
+    int SY;           // node rows per plane = H + 1
+    long long nplane; // node plane stride  = P * SY
+    long long cplane; // cell plane stride  = W * H
+    int zlo;          // global z of the first stored plane (0 on a single GPU)
+    int nzc;          // stored cell planes  [zlo, zlo + nzc)
+    int nzn;          // stored node planes  [zlo, zlo + nzn), nzn = nzc + 1
+};
+
+// stencil code byte per cell, derived from the mask after every fill
+enum : unsigned {
+    CODE_SX0 = 1u, CODE_SX1 = 2u, CODE_SY0 = 4u, CODE_SY1 = 8u, CODE_SZ0 = 16u, CODE_SZ1 = 32u,
+    CODE_ACTIVE = 64u, // interior fluid cell with at least one fluid neighbour: updated by the pressure sweeps
+    CODE_SELF = 128u   // the cell itself is fluid
+};
+
+#define SMK_MAX_OBJ 16
+struct ObjP {
+    int nsrc, nobs;
+    float src[SMK_MAX_OBJ][4]; // x, y, z, r           (cu:721-727)
+    float obs[SMK_MAX_OBJ][4]; // x, y, z, r  (the obstacle velocity is never read by a kernel, cu:299-301)
+};

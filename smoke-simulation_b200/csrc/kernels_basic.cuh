@@ -1,0 +1,387 @@
+// kernels_basic.cuh -- one-stage-per-launch sm_100a kernels of the smoke step.
+//
+// These are the straightforward streaming kernels: every thread owns one cell / node of an x-fastest
+// row, all global accesses of a warp are unit-stride.  They are the parity baseline for the fused /
+// temporally blocked kernels and the path used for grids those kernels do not cover.
+//
+// Arithmetic contract: every floating-point operation below is spelled with an explicit rounding
+// intrinsic (__fmul_rn / __fadd_rn / __fmaf_rn / __fdiv_rn / __dmul_rn ...) in exactly the order and
+// fusion pattern that nvcc 12.9 generates for the reference kernels on sm_100a (read off the SASS of
+// project/smokeSimulation.cu; the pattern is restated at each function).  The compiler can therefore
+// neither contract nor re-associate anything, and results are bit-identical to the reference step.
+#pragma once
+#include <cuda_runtime.h>
+#include "grid.h"
+
+namespace smk {
+
+__device__ __forceinline__ long long node_index(const GridP& g, int x, int y, int z)
+{
+    return (long long)x + (long long)y * g.P + (long long)(z - g.zlo) * g.nplane;
+}
+__device__ __forceinline__ long long cell_index(const GridP& g, int x, int y, int z)
+{
+    return (long long)x + (long long)y * g.W + (long long)(z - g.zlo) * g.cplane;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Source + obstacle fill.  Reference: fillSmoke cu:251-273, fillObstacle cu:289-313, drawObjects
+// cu:714-771.  Interior cells only.  dist = powf(x-sx,2)+powf(y-sy,2)+powf(z-sz,2) with the cell
+// coordinate converted int->float first; the same libdevice powf as the reference (mask ties, H4).
+// Sources: dist < r*r  =>  density 1.0 in BOTH buffers.  Obstacles: the cell is rewritten for every
+// obstacle in order, so the last obstacle decides; with no obstacle the mask is left alone.
+// One thread per cell of an x-row; grid.y walks the z planes [za, zb).
+__global__ void __launch_bounds__(256) k_fill(GridP g, float* __restrict__ smoke0, float* __restrict__ smoke1,
+                                              unsigned char* __restrict__ mask, ObjP o, int za)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.W * g.H) return;
+    const int y = i / g.W, x = i - y * g.W;
+    const int z = za + blockIdx.y;
+    if (x < 1 || y < 1 || z < 1 || x >= g.W - 1 || y >= g.H - 1 || z >= g.D - 1) return;
+    const long long c = cell_index(g, x, y, z);
+    for (int k = 0; k < o.nsrc; k++) {
+        float dist = powf(x - o.src[k][0], 2) + powf(y - o.src[k][1], 2) + powf(z - o.src[k][2], 2);
+        if (dist < o.src[k][3] * o.src[k][3]) {
+            smoke0[c] = 1.0f;
+            smoke1[c] = 1.0f;
+        }
+    }
+    if (o.nobs > 0) {
+        unsigned char sv = 1;
+        for (int k = 0; k < o.nobs; k++) {
+            float dist = powf(x - o.obs[k][0], 2) + powf(y - o.obs[k][1], 2) + powf(z - o.obs[k][2], 2);
+            sv = (dist < o.obs[k][3] * o.obs[k][3]) ? 0 : 1;
+        }
+        mask[c] = sv;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Stencil codes.  Not a reference kernel: it folds the seven mask reads of divergence (cu:365-376)
+// and the "both cells fluid" tests of integrate / advection (cu:321, 534, 564, 594, 623) into one byte
+// per cell so that the hot kernels read 1 B/cell of mask information.  Neighbours outside the domain (or
+// outside the stored slab) count as solid; such cells are never ACTIVE.
+__global__ void __launch_bounds__(256) k_codes(GridP g, const unsigned char* __restrict__ mask,
+                                               unsigned char* __restrict__ code, int za)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.W * g.H) return;
+    const int y = i / g.W, x = i - y * g.W;
+    const int z = za + blockIdx.y;
+    const long long c = cell_index(g, x, y, z);
+    const int zhi = g.zlo + g.nzc; // first cell plane not stored
+    unsigned v = 0;
+    if (x > 0 && mask[c - 1]) v |= CODE_SX0;
+    if (x < g.W - 1 && mask[c + 1]) v |= CODE_SX1;
+    if (y > 0 && mask[c - g.W]) v |= CODE_SY0;
+    if (y < g.H - 1 && mask[c + g.W]) v |= CODE_SY1;
+    if (z > g.zlo && mask[c - g.cplane]) v |= CODE_SZ0;
+    if (z < zhi - 1 && mask[c + g.cplane]) v |= CODE_SZ1;
+    const bool interior = x >= 1 && y >= 1 && z >= 1 && x < g.W - 1 && y < g.H - 1 && z < g.D - 1;
+    const bool self = mask[c] != 0;
+    if (self) v |= CODE_SELF;
+    if (interior && self && (v & 63u)) v |= CODE_ACTIVE;
+    code[c] = (unsigned char)v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Forcing + clamp, fused (both are pointwise on the same staggered index).
+// integrate cu:315-329: v-face (x,y,z), x<W, 1<=y<H, z<D, cell and the cell below fluid:
+//     v += smoke*gravity*dt + (alpha*smoke)*dt
+//   SASS: t = fma(smoke*gravity, dt, (smoke*alpha)*dt);  v = t + v
+// velocityConfinement cu:331-352 (max-velocity clamp): 1<=x<W, 1<=y<H, 1<=z<D, same index for u,v,w:
+//     L = u*u+v*v+w*w;  if (L*dt > 9)  u,v,w *= 9/(L*dt)
+//   SASS: L = fma(w,w, fma(u,u, v*v));  t = L*dt;  k = 9/t (IEEE);  three FMULs
+// One thread per node of a row; grid.y walks node planes [za, zb).
+__global__ void __launch_bounds__(256) k_force_clamp(GridP g, float* __restrict__ u, float* __restrict__ v,
+                                                     float* __restrict__ w, const float* __restrict__ smoke,
+                                                     const unsigned char* __restrict__ code, float dt, float gravity,
+                                                     float alpha, int za)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.P * g.SY) return;
+    const int y = i / g.P, x = i - y * g.P;
+    const int z = za + blockIdx.y;
+    if (x >= g.W || y < 1 || y >= g.H || z >= g.D) return;
+    const long long n = node_index(g, x, y, z);
+    float vv = v[n];
+    bool dirty = false;
+    {
+        const long long c = cell_index(g, x, y, z);
+        const unsigned cd = code[c];
+        if ((cd & CODE_SELF) && (cd & CODE_SY0)) {
+            const float d = smoke[c];
+            const float t = __fmaf_rn(__fmul_rn(d, gravity), dt, __fmul_rn(__fmul_rn(d, alpha), dt));
+            vv = __fadd_rn(t, vv);
+            dirty = true;
+        }
+    }
+    if (x >= 1 && z >= 1) {
+        const float uu = u[n], ww = w[n];
+        const float L = __fmaf_rn(ww, ww, __fmaf_rn(uu, uu, __fmul_rn(vv, vv)));
+        const float t = __fmul_rn(L, dt);
+        if (t > 9.0f) {
+            const float k = __fdiv_rn(9.0f, t);
+            u[n] = __fmul_rn(uu, k);
+            w[n] = __fmul_rn(ww, k);
+            vv = __fmul_rn(vv, k);
+            dirty = true;
+        }
+    }
+    if (dirty) v[n] = vv;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The pressure update of ONE cell (divergence cu:356-394), shared by every pressure kernel.
+//   div = ((((-u0 + u1) - v0) + v1) - w0) + w1                       (cu:379-381, left to right)
+//   p   = (float)((double)(div / acc) * -1.9)   == (float)((double)(-div/acc) * 1.9)   (cu:384; the
+//         reference SASS folds the negation into the constant: DMUL by -1.9)
+//   u0 -= p*sx0  ...  w1 += p*sz1;   p*s is exact (s in {0,1}) so each update is one rounding.
+__device__ __forceinline__ float pressure_p(float u0, float u1, float v0, float v1, float w0, float w1, int acc)
+{
+    float div = __fadd_rn(-u0, u1);
+    div = __fadd_rn(div, -v0);
+    div = __fadd_rn(div, v1);
+    div = __fadd_rn(div, -w0);
+    div = __fadd_rn(div, w1);
+    const float q = __fdiv_rn(div, (float)acc);
+    return __double2float_rn(__dmul_rn((double)q, -1.9));
+}
+
+// One red or black half-sweep, in place (cu:356-394; schedule cu:797-801).
+// offset 0 <-> (x+y+z) even, 1 <-> odd.  One thread per PAIR of x-adjacent cells: exactly one cell of
+// the pair has the active colour, so a warp covers 64 consecutive cells of a row and every lane works.
+// Same-colour cells share no face => race-free in place.
+__global__ void __launch_bounds__(256) k_pressure_half(GridP g, float* __restrict__ u, float* __restrict__ v,
+                                                       float* __restrict__ w, const unsigned char* __restrict__ code,
+                                                       int offset, int za)
+{
+    const int halfW = (g.W + 1) >> 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= halfW * g.H) return;
+    const int y = i / halfW, xp = i - y * halfW;
+    const int z = za + blockIdx.y;
+    const int x = 2 * xp + ((y + z + offset) & 1);
+    if (x >= g.W) return;
+    const unsigned cd = code[cell_index(g, x, y, z)];
+    if (!(cd & CODE_ACTIVE)) return;
+    const int acc = __popc(cd & 63u);
+    const long long n = node_index(g, x, y, z);
+    const long long nx = n + 1, ny = n + g.P, nz = n + g.nplane;
+    const float u0 = u[n], u1 = u[nx], v0 = v[n], v1 = v[ny], w0 = w[n], w1 = w[nz];
+    const float p = pressure_p(u0, u1, v0, v1, w0, w1, acc);
+    if (cd & CODE_SX0) u[n] = __fsub_rn(u0, p);
+    if (cd & CODE_SX1) u[nx] = __fadd_rn(u1, p);
+    if (cd & CODE_SY0) v[n] = __fsub_rn(v0, p);
+    if (cd & CODE_SY1) v[ny] = __fadd_rn(v1, p);
+    if (cd & CODE_SZ0) w[n] = __fsub_rn(w0, p);
+    if (cd & CODE_SZ1) w[nz] = __fadd_rn(w1, p);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Clamped trilinear sample (sampleSmoke cu:451-484).  Clamp bounds (bx,by,bz) = cell dims - 1 as floats,
+// also for staggered fields; (sy, sz) are the strides of the sampled array; zlo its first stored plane.
+//   p = max(min(pos, b), 1);  q = p - delta;  i0 = (int)min(floor(q), b);  w1 = q - i0;  w0 = 1 - w1;
+//   i1 = (int)min(i0 + 1, b)
+// SASS: weights ((xw*yw)*zw) by FMULs; acc = RN(w100*f100); then FFMA for 000,010,110,001,101,011,111.
+struct Tri {
+    int x0, x1, y0, y1, z0, z1;
+    float xw0, xw1, yw0, yw1, zw0, zw1;
+};
+__device__ __forceinline__ void tri_axis(float pos, float delta, float b, int& i0, int& i1, float& w0, float& w1)
+{
+    const float p = fmaxf(fminf(pos, b), 1.0f);
+    const float q = __fadd_rn(p, -delta);
+    i0 = (int)fminf(floorf(q), b);
+    w1 = __fadd_rn(q, -(float)i0);
+    w0 = __fadd_rn(1.0f, -w1);
+    i1 = (int)fminf((float)(i0 + 1), b);
+}
+__device__ __forceinline__ float tri_combine(const Tri& t, float f000, float f100, float f010, float f110,
+                                             float f001, float f101, float f011, float f111)
+{
+    const float a00 = __fmul_rn(t.xw0, t.yw0), a10 = __fmul_rn(t.xw1, t.yw0);
+    const float a01 = __fmul_rn(t.xw0, t.yw1), a11 = __fmul_rn(t.xw1, t.yw1);
+    float acc = __fmul_rn(__fmul_rn(a10, t.zw0), f100);
+    acc = __fmaf_rn(__fmul_rn(a00, t.zw0), f000, acc);
+    acc = __fmaf_rn(__fmul_rn(a01, t.zw0), f010, acc);
+    acc = __fmaf_rn(__fmul_rn(a11, t.zw0), f110, acc);
+    acc = __fmaf_rn(__fmul_rn(a00, t.zw1), f001, acc);
+    acc = __fmaf_rn(__fmul_rn(a10, t.zw1), f101, acc);
+    acc = __fmaf_rn(__fmul_rn(a01, t.zw1), f011, acc);
+    acc = __fmaf_rn(__fmul_rn(a11, t.zw1), f111, acc);
+    return acc;
+}
+__device__ __forceinline__ float sample_global(const float* __restrict__ f, long long sy, long long sz, int zlo,
+                                               float px, float py, float pz, float dx, float dy, float dz,
+                                               float bx, float by, float bz)
+{
+    Tri t;
+    tri_axis(px, dx, bx, t.x0, t.x1, t.xw0, t.xw1);
+    tri_axis(py, dy, by, t.y0, t.y1, t.yw0, t.yw1);
+    tri_axis(pz, dz, bz, t.z0, t.z1, t.zw0, t.zw1);
+    const float* r00 = f + t.y0 * sy + (long long)(t.z0 - zlo) * sz;
+    const float* r10 = f + t.y1 * sy + (long long)(t.z0 - zlo) * sz;
+    const float* r01 = f + t.y0 * sy + (long long)(t.z1 - zlo) * sz;
+    const float* r11 = f + t.y1 * sy + (long long)(t.z1 - zlo) * sz;
+    return tri_combine(t, r00[t.x0], r00[t.x1], r10[t.x0], r10[t.x1], r01[t.x0], r01[t.x1], r11[t.x0], r11[t.x1]);
+}
+
+// 8-point face sums (avgU/avgV/avgW cu:409-447) in source order, then *0.125 (= /8 exactly).
+// f points at node (x,y,z); P = row pitch, S = plane stride.
+__device__ __forceinline__ float avg_u8(const float* __restrict__ f, long long P, long long S)
+{
+    float a = f[-S];
+    a = __fadd_rn(a, f[1 - S]);
+    a = __fadd_rn(a, f[-P - S]);
+    a = __fadd_rn(a, f[1 - P - S]);
+    a = __fadd_rn(a, f[0]);
+    a = __fadd_rn(a, f[1]);
+    a = __fadd_rn(a, f[-P]);
+    a = __fadd_rn(a, f[1 - P]);
+    return __fmul_rn(a, 0.125f);
+}
+__device__ __forceinline__ float avg_v8(const float* __restrict__ f, long long P, long long S)
+{
+    float a = f[-S];
+    a = __fadd_rn(a, f[-1 - S]);
+    a = __fadd_rn(a, f[P - S]);
+    a = __fadd_rn(a, f[P - 1 - S]);
+    a = __fadd_rn(a, f[0]);
+    a = __fadd_rn(a, f[-1]);
+    a = __fadd_rn(a, f[P]);
+    a = __fadd_rn(a, f[P - 1]);
+    return __fmul_rn(a, 0.125f);
+}
+__device__ __forceinline__ float avg_w8(const float* __restrict__ f, long long P, long long S)
+{
+    float a = f[0];
+    a = __fadd_rn(a, f[-1]);
+    a = __fadd_rn(a, f[-P]);
+    a = __fadd_rn(a, f[-P - 1]);
+    a = __fadd_rn(a, f[-S]);
+    a = __fadd_rn(a, f[-1 - S]);
+    a = __fadd_rn(a, f[-P - S]);
+    a = __fadd_rn(a, f[-P - 1 - S]);
+    return __fmul_rn(a, 0.125f);
+}
+
+// (float)((double)i + 0.5): the reference evaluates "y + 0.5" in double and narrows (cu:536-537)
+__device__ __forceinline__ float half_up(int i) { return __double2float_rn(__dadd_rn((double)i, 0.5)); }
+
+// ---------------------------------------------------------------------------------------------------
+// Self-advection of u, v, w in ONE kernel (velocityAdvectionU/V/W cu:527-615), now -> past.
+//   U: 1<=x<W,  1<=y<H-1, 1<=z<D-1, s[x]&&s[x-1];  pos0 = (x, y+.5, z+.5);  vel = (u, avgV, avgW)
+//   V: 1<=x<W-1, 1<=y<H,  1<=z<D-1, s[y]&&s[y-1];  pos0 = (x+.5, y, z+.5);  vel = (avgU, v, avgW)
+//   W: 1<=x<W-1, 1<=y<H-1, 1<=z<D,  s[z]&&s[z-1];  pos0 = (x+.5, y+.5, z);  vel = (avgU, avgV, w)
+//   pos = pos0 - dt*vel   SASS: fma(-vel, dt, pos0)
+// Faces that fail the test are NOT written (the destination keeps its old value).
+// The three 8-point sums are shared between the components that use them (identical values).
+__global__ void __launch_bounds__(256) k_advect_velocity(GridP g, const float* __restrict__ u0,
+                                                         const float* __restrict__ v0, const float* __restrict__ w0,
+                                                         float* __restrict__ u1, float* __restrict__ v1,
+                                                         float* __restrict__ w1, const unsigned char* __restrict__ code,
+                                                         float dt, int za)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.P * g.SY) return;
+    const int y = i / g.P, x = i - y * g.P;
+    const int z = za + blockIdx.y;
+    if (x < 1 || y < 1 || z < 1 || x >= g.W || y >= g.H || z >= g.D) return;
+    const unsigned cd = code[cell_index(g, x, y, z)];
+    if (!(cd & CODE_SELF)) return;
+    const bool doU = (cd & CODE_SX0) && y < g.H - 1 && z < g.D - 1;
+    const bool doV = (cd & CODE_SY0) && x < g.W - 1 && z < g.D - 1;
+    const bool doW = (cd & CODE_SZ0) && x < g.W - 1 && y < g.H - 1;
+    if (!(doU || doV || doW)) return;
+    const long long n = node_index(g, x, y, z);
+    const long long P = g.P, S = g.nplane;
+    const float bx = (float)(unsigned)(g.W - 1), by = (float)(unsigned)(g.H - 1), bz = (float)(unsigned)(g.D - 1);
+    float au = 0.f, av = 0.f, aw = 0.f;
+    if (doV || doW) au = avg_u8(u0 + n, P, S);
+    if (doU || doW) av = avg_v8(v0 + n, P, S);
+    if (doU || doV) aw = avg_w8(w0 + n, P, S);
+    const float xh = half_up(x), yh = half_up(y), zh = half_up(z);
+    if (doU) {
+        const float px = __fmaf_rn(-u0[n], dt, (float)x);
+        const float py = __fmaf_rn(-av, dt, yh);
+        const float pz = __fmaf_rn(-aw, dt, zh);
+        u1[n] = sample_global(u0, P, S, g.zlo, px, py, pz, 0.f, .5f, .5f, bx, by, bz);
+    }
+    if (doV) {
+        const float px = __fmaf_rn(-au, dt, xh);
+        const float py = __fmaf_rn(-v0[n], dt, (float)y);
+        const float pz = __fmaf_rn(-aw, dt, zh);
+        v1[n] = sample_global(v0, P, S, g.zlo, px, py, pz, .5f, 0.f, .5f, bx, by, bz);
+    }
+    if (doW) {
+        const float px = __fmaf_rn(-au, dt, xh);
+        const float py = __fmaf_rn(-av, dt, yh);
+        const float pz = __fmaf_rn(-w0[n], dt, (float)z);
+        w1[n] = sample_global(w0, P, S, g.zlo, px, py, pz, .5f, .5f, 0.f, bx, by, bz);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Density advection (advectSmoke cu:617-638) with the NEW velocities (cu:810).  Interior fluid cells.
+//   u_t = (u[x]+u[x+1])/2;  pos = (float)(((double)x + 0.5) - (double)(u_t*dt))
+//   SASS: h = (a+b) * -0.5;  m = h*dt;  pos = (float)(((double)x + 0.5) + (double)m)
+__global__ void __launch_bounds__(256) k_advect_smoke(GridP g, const float* __restrict__ s0, float* __restrict__ s1,
+                                                      const float* __restrict__ u, const float* __restrict__ v,
+                                                      const float* __restrict__ w, const unsigned char* __restrict__ code,
+                                                      float dt, int za)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.W * g.H) return;
+    const int y = i / g.W, x = i - y * g.W;
+    const int z = za + blockIdx.y;
+    if (x < 1 || y < 1 || z < 1 || x >= g.W - 1 || y >= g.H - 1 || z >= g.D - 1) return;
+    const long long c = cell_index(g, x, y, z);
+    if (!(code[c] & CODE_SELF)) return;
+    const long long n = node_index(g, x, y, z);
+    const float mu = __fmul_rn(__fmul_rn(__fadd_rn(u[n], u[n + 1]), -0.5f), dt);
+    const float mv = __fmul_rn(__fmul_rn(__fadd_rn(v[n], v[n + g.P]), -0.5f), dt);
+    const float mw = __fmul_rn(__fmul_rn(__fadd_rn(w[n], w[n + g.nplane]), -0.5f), dt);
+    const float px = __double2float_rn(__dadd_rn(__dadd_rn((double)x, 0.5), (double)mu));
+    const float py = __double2float_rn(__dadd_rn(__dadd_rn((double)y, 0.5), (double)mv));
+    const float pz = __double2float_rn(__dadd_rn(__dadd_rn((double)z, 0.5), (double)mw));
+    const float bx = (float)(unsigned)(g.W - 1), by = (float)(unsigned)(g.H - 1), bz = (float)(unsigned)(g.D - 1);
+    s1[c] = sample_global(s0, g.W, g.cplane, g.zlo, px, py, pz, .5f, .5f, .5f, bx, by, bz);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// max |div| over interior fluid cells (residual the reference never computes; formula cu:379-381).
+// Warp-shuffle reduction, one atomicMax per block on the float's bit pattern (values are >= 0).
+__global__ void __launch_bounds__(256) k_max_divergence(GridP g, const float* __restrict__ u, const float* __restrict__ v,
+                                                        const float* __restrict__ w, const unsigned char* __restrict__ code,
+                                                        unsigned* __restrict__ out, int za)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float m = 0.f;
+    if (i < g.W * g.H) {
+        const int y = i / g.W, x = i - y * g.W;
+        const int z = za + blockIdx.y;
+        if (x >= 1 && y >= 1 && z >= 1 && x < g.W - 1 && y < g.H - 1 && z < g.D - 1 &&
+            (code[cell_index(g, x, y, z)] & CODE_SELF)) {
+            const long long n = node_index(g, x, y, z);
+            float div = __fadd_rn(-u[n], u[n + 1]);
+            div = __fadd_rn(div, -v[n]);
+            div = __fadd_rn(div, v[n + g.P]);
+            div = __fadd_rn(div, -w[n]);
+            div = __fadd_rn(div, w[n + g.nplane]);
+            m = fabsf(div);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.f;
+        for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+    }
+}
+
+} // namespace smk

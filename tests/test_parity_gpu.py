@@ -1,0 +1,207 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of
+libsmoke_b200.so.  Checkers: oracle/liboracle.so (contract=1 = the FMA pattern nvcc applies to the
+reference), the committed golden fixtures (reference kernel bodies, uncontracted) and -- when the
+snapshot carries it -- the reference step itself built headless for sm_100a (oracle/_ref/libref_gpu.so).
+
+Bars: mask bit-exact; fields max|a-b|/max|b| <= 1e-5; against the contracted oracle and
+the GPU reference the kernels are written to be bit-identical, which is asserted as exact equality."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, all_fields, inject, random_state, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+SMALL_SCENE = (20, 18, 16, -9.82, 2.0, [(10.0, 8.0, 8.0, 3.0)], [(13.0, 4.0, 9.0, 3.0), (6.0, 6.0, 5.0, 2.5)])
+SMALL_RANDOM = (17, 21, 19, -9.82, 6.0, [(8.0, 9.0, 9.0, 2.5)], [])
+
+
+def make_pair(po, smk, scene, state=None, contract=1):
+    W, H, D = scene[:3]
+    a = smk.SmokeSim(W, H, D)
+    b = po.Oracle(W, H, D, contract=contract)
+    for e in (a, b):
+        po.setup_scene(e, scene)
+        if state is not None:
+            inject(po, e, state)
+    return a, b
+
+
+def compare(po, a, b, what, exact=True):
+    fa, fb = all_fields(po, a), all_fields(po, b)
+    assert np.array_equal(fa["mask"], fb["mask"]), f"{what}: mask differs in {(fa['mask'] != fb['mask']).sum()} cells"
+    worst = 0.0
+    for k in fa:
+        if k == "mask":
+            continue
+        if exact:
+            bad = fa[k] != fb[k]
+            assert not bad.any(), f"{what}: {k} differs in {int(bad.sum())} entries, rel {rel_err(fa[k], fb[k]):.3e}"
+        else:
+            e = rel_err(fa[k], fb[k])
+            worst = max(worst, e)
+            assert e <= TOL, f"{what}: {k} rel err {e:.3e} > {TOL}"
+    return worst
+
+
+@pytest.mark.parametrize("dims", [(17, 21, 19), (8, 9, 33), (3, 3, 3), (4, 5, 3), (33, 16, 10), (64, 20, 12)])
+def test_stage_by_stage_vs_oracle_random_fields(po, smk, dims):
+    """Per-kernel parity on random u/v/w/density and a random mask, ragged non-cubic sizes included."""
+    W, H, D = dims
+    scene = (W, H, D, -9.82, 3.0, [(W / 2, H / 2, D / 2, 2.0)], [])
+    st = random_state(po, W, H, D, seed=11)
+    a, b = make_pair(po, smk, scene, st)
+    dt = 0.05
+    a.flip(); b.flip()
+    a.fill(); b.fill()
+    compare(po, a, b, f"{dims} fill")
+    a.force_clamp(dt); b.integrate(dt); b.clamp(dt)
+    compare(po, a, b, f"{dims} force+clamp")
+    for off in (0, 1, 0, 1):
+        a.pressure_halfsweep(off); b.pressure_halfsweep(off)
+        compare(po, a, b, f"{dims} halfsweep {off}")
+    a.advect_velocity(dt); b.advect_velocity(dt)
+    compare(po, a, b, f"{dims} advect velocity")
+    a.advect_smoke(dt); b.advect_smoke(dt)
+    compare(po, a, b, f"{dims} advect smoke")
+    a.close()
+
+
+def test_clamp_engages(po, smk):
+    """Large velocities so that the max-velocity clamp (cu:331-352) actually fires."""
+    W, H, D = 12, 10, 9
+    st = random_state(po, W, H, D, seed=5)
+    for k in ("u", "v", "w"):
+        st[k] *= 20.0
+    a, b = make_pair(po, smk, (W, H, D, -9.82, 2.0, [], []), st)
+    a.flip(); b.flip(); a.fill(); b.fill()
+    before = a.get_field(po.U, po.NOW).copy()
+    a.force_clamp(0.05); b.integrate(0.05); b.clamp(0.05)
+    assert (a.get_field(po.U, po.NOW) != before).any()
+    compare(po, a, b, "clamp")
+    a.close()
+
+
+@pytest.mark.parametrize("scene,ticks,rand", [(SMALL_SCENE, 6, False), (SMALL_RANDOM, 3, True)])
+def test_full_step_vs_oracle_and_golden(po, smk, scene, ticks, rand):
+    st = random_state(po, *scene[:3]) if rand else None
+    a, b = make_pair(po, smk, scene, st)
+    host = np.zeros((scene[2], scene[1], scene[0]), dtype=np.float32)
+    for t in range(ticks):
+        a.step(po.tick_dt(t), host); b.step(po.tick_dt(t))
+    compare(po, a, b, "full step vs oracle(contract=1)")
+    assert np.array_equal(host, a.get_field(po.SMOKE, po.PAST)), "host readback != device density"
+    g = np.load(os.path.join(GOLDEN, ("small_random" if rand else "small_scene") + ".npz"))
+    fa = all_fields(po, a)
+    assert np.array_equal(fa["mask"], g["mask"])
+    for k in fa:
+        if k != "mask":
+            assert rel_err(fa[k], g[k]) <= TOL, (k, rel_err(fa[k], g[k]))
+    a.close()
+
+
+def test_c1_default_scene_20_ticks(po, smk):
+    """BASELINE configs[0]: 80^3 default scene, 20 ticks, against the oracle (exact) and the golden fixture
+    from the reference bodies (mask bit-exact, fields <= 1e-5, same final divergence residual)."""
+    sc = po.SCENES["C1"]
+    a, b = make_pair(po, smk, sc)
+    for t in range(20):
+        a.step(po.tick_dt(t)); b.step(po.tick_dt(t))
+    compare(po, a, b, "C1 vs oracle(contract=1)")
+    g = np.load(os.path.join(GOLDEN, "c1_80.npz"))
+    mask = a.get_field(po.MASK)
+    assert np.array_equal(np.packbits(mask), g["mask_bits"]) and int((mask == 0).sum()) == 15058
+    assert rel_err(a.get_field(po.SMOKE, po.PAST), g["density"]) <= TOL
+    u, v, w = (a.get_field(f, po.NOW) for f in (po.U, po.V, po.W))
+    for got, key in ((u[:, 40, :], "u_y40"), (v[:, 40, :], "v_y40"), (w[:, 40, :], "w_y40"), (u[40], "u_z40"), (v[40], "v_z40"), (w[40], "w_z40")):
+        assert rel_err(got, g[key]) <= TOL, key
+    res = a.max_divergence()
+    assert abs(res - b.max_divergence()) == 0.0
+    assert abs(res - float(g["maxdiv"])) <= 1e-5 * max(1.0, float(g["absmax"].max()))
+    a.close()
+
+
+def test_vs_reference_gpu_build(po, smk):
+    """The reference step itself on the same GPU (oracle/_ref/libref_gpu.so): C1 for 20 ticks and a random
+    state stage by stage.  Mask bit-exact, fields identical."""
+    if not po.have_ref_gpu():
+        pytest.skip("oracle/_ref/libref_gpu.so not in the snapshot")
+    sc = po.SCENES["C1"]
+    a = smk.SmokeSim(*sc[:3]); po.setup_scene(a, sc)
+    r = po.RefGPU(*sc[:3]); po.setup_scene(r, sc)
+    try:
+        for t in range(20):
+            a.step(po.tick_dt(t)); r.step(po.tick_dt(t))
+        compare(po, a, r, "C1 vs reference on GPU")
+        assert np.array_equal(r.host, a.get_field(po.SMOKE, po.PAST))
+    finally:
+        r.close(); a.close()
+    W, H, D = 33, 20, 17
+    scene = (W, H, D, -9.82, 3.0, [(16.0, 10.0, 8.0, 3.0)], [])
+    st = random_state(po, W, H, D, seed=21)
+    a = smk.SmokeSim(W, H, D); po.setup_scene(a, scene); inject(po, a, st)
+    r = po.RefGPU(W, H, D); po.setup_scene(r, scene); inject(po, r, st)
+    try:
+        a.flip(); r.flip(); a.fill(); r.fill()
+        a.force_clamp(0.05); r.integrate(0.05); r.clamp(0.05)
+        compare(po, a, r, "random: force+clamp vs reference GPU")
+        for off in (0, 1, 0, 1):
+            a.pressure_halfsweep(off); r.pressure_halfsweep(off)
+        compare(po, a, r, "random: half-sweeps vs reference GPU")
+        a.advect_velocity(0.05); r.advect_velocity(0.05)
+        a.advect_smoke(0.05); r.advect_smoke(0.05)
+        compare(po, a, r, "random: advection vs reference GPU")
+    finally:
+        r.close(); a.close()
+
+
+def test_moving_obstacle_and_last_wins(po, smk):
+    W = H = D = 16
+    a = smk.SmokeSim(W, H, D); b = po.Oracle(W, H, D)
+    ids = []
+    for e in (a, b):
+        e.add_source(8, 4, 8, 2.0)
+        e.add_obstacle(5, 5, 5, 0, 0, 0, 2.5)
+        ids.append(e.add_obstacle(10, 10, 10, 0, 0, 0, 2.5))
+    assert ids[0] == ids[1] == 2
+    for t in range(3):
+        a.step(po.tick_dt(t)); b.step(po.tick_dt(t))
+    for e in (a, b):
+        e.update_object_pos(2, 6, 9, 6)
+    for t in range(3):
+        a.step(0.05); b.step(0.05)
+    compare(po, a, b, "moving obstacle")
+    m = a.get_field(po.MASK)
+    assert m[5, 5, 5] == 1 and m[10, 10, 10] == 1 and m[6, 9, 6] == 0
+    a.close()
+
+
+def test_empty_scene_and_parameters(po, smk):
+    a = smk.SmokeSim(9, 7, 5)
+    for t in range(2):
+        a.step(po.tick_dt(t))
+    f = all_fields(po, a)
+    assert all(float(np.abs(f[k]).max()) == 0.0 for k in f if k != "mask")
+    assert abs(a.gravity + 9.82) < 1e-6 and a.buoyancy == 2.0
+    a.gravity = 3.0
+    assert a.gravity == 3.0
+    assert a.launch_count() > 0
+    a.close()
+
+
+def test_c2_256_one_tick_property_checks(po, smk):
+    """BASELINE configs[1] size (256^3): two ticks against the oracle (exact), plus size-independent
+    properties: density stays in [0,1], the residual drops, untouched boundary faces stay zero."""
+    sc = po.SCENES["C2"]
+    a, b = make_pair(po, smk, sc)
+    for t in range(2):
+        a.step(po.tick_dt(t)); b.step(po.tick_dt(t))
+    compare(po, a, b, "C2 256^3, 2 ticks")
+    d = a.get_field(po.SMOKE, po.PAST)
+    assert d.min() >= 0.0 and d.max() <= 1.0
+    u = a.get_field(po.U, po.NOW)
+    assert np.abs(u[:, :, 0]).max() == 0.0 and np.abs(u[:, :, -1]).max() == 0.0 and np.abs(u[0]).max() == 0.0
+    a.close()
