@@ -227,7 +227,11 @@ def main():
     sim = smk.SmokeSim(W, H, D)
     po.setup_scene(sim, scene)
     sim.set_solver(0, 30, args.fuse)
-    stream = torch.cuda.current_stream()
+    # the library runs the whole step on ONE stream; hand it a real (non-default) torch stream so that
+    # torch.cuda.Event brackets exactly the work of the step
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     sim.set_stream(stream.cuda_stream)
     host = torch.empty((D, H, W), dtype=torch.float32, pin_memory=True)
     host_ptr = host.data_ptr()

@@ -201,7 +201,7 @@ def test_c2_256_one_tick_property_checks(po, smk):
         a.step(po.tick_dt(t)); b.step(po.tick_dt(t))
     compare(po, a, b, "C2 256^3, 2 ticks")
     d = a.get_field(po.SMOKE, po.PAST)
-    assert d.min() >= 0.0 and d.max() <= 1.0
+    assert d.min() >= 0.0 and d.max() <= 1.0 + 1e-6  # trilinear weights sum to 1 within an ulp
     u = a.get_field(po.U, po.NOW)
     assert np.abs(u[:, :, 0]).max() == 0.0 and np.abs(u[:, :, -1]).max() == 0.0 and np.abs(u[0]).max() == 0.0
     a.close()
