@@ -290,6 +290,8 @@ def main():
         cells = W * H * D
         alg_bytes = BYTES_PER_CELL_HALFSWEEP * cells
         halfsweeps_per_launch = 60 * K / max(p_launches, 1)
+        # compulsory bytes of ONE launch: u,v,w read + write and 1 B of mask information per cell (B(k) model
+        # of SURVEY.md section 8(d)); a launch that fuses k half-sweeps does k x the reference's work on those bytes
         achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
         roofline = {
             "bound": "hbm", "kernel": "pressure half-sweep (red-black SOR on u,v,w)", "achieved": achieved, "peak": peak,

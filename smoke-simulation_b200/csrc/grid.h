@@ -1,6 +1,7 @@
 // grid.h -- HBM data layout shared by the host code and the kernels.
 //
-// Cell fields (density, mask, stencil code): the reference layout, c = x + y*W + (z-zlo)*W*H.
+// Cell fields (density, mask): the reference layout, c = x + y*W + (z-zlo)*W*H.  The derived stencil-code
+// array has its own padded pitch, k = x + y*PC + (z-zlo)*PC*H, so 2- and 16-byte accesses are aligned.
 // Staggered fields (u, v, w): "node" layout with a padded row pitch so that every row starts on a
 // 32-byte sector and TMA / float4 access is legal: n = x + y*P + (z-zlo)*P*(H+1), P = roundup(W+1, 8).
 // Node (x,y,z) holds the three LOW faces of cell (x,y,z): u[x,y,z] between cells x-1|x, v between
@@ -18,6 +19,8 @@ struct GridP {
     int zlo;          // global z of the first stored plane (0 on a single GPU)
     int nzc;          // stored cell planes  [zlo, zlo + nzc)
     int nzn;          // stored node planes  [zlo, zlo + nzn), nzn = nzc + 1
+    int PC;           // row pitch of the stencil-code array in bytes = roundup(W, 16) (pad bytes are 0)
+    long long kplane; // plane stride of the stencil-code array = PC * H
 };
 
 // stencil code byte per cell, derived from the mask after every fill

@@ -23,6 +23,10 @@ __device__ __forceinline__ long long cell_index(const GridP& g, int x, int y, in
 {
     return (long long)x + (long long)y * g.W + (long long)(z - g.zlo) * g.cplane;
 }
+__device__ __forceinline__ long long code_index(const GridP& g, int x, int y, int z)
+{
+    return (long long)x + (long long)y * g.PC + (long long)(z - g.zlo) * g.kplane;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Source + obstacle fill.  Reference: fillSmoke cu:251-273, fillObstacle cu:289-313, drawObjects
@@ -82,7 +86,7 @@ __global__ void __launch_bounds__(256) k_codes(GridP g, const unsigned char* __r
     const bool self = mask[c] != 0;
     if (self) v |= CODE_SELF;
     if (interior && self && (v & 63u)) v |= CODE_ACTIVE;
-    code[c] = (unsigned char)v;
+    code[code_index(g, x, y, z)] = (unsigned char)v;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -108,10 +112,9 @@ __global__ void __launch_bounds__(256) k_force_clamp(GridP g, float* __restrict_
     float vv = v[n];
     bool dirty = false;
     {
-        const long long c = cell_index(g, x, y, z);
-        const unsigned cd = code[c];
+        const unsigned cd = code[code_index(g, x, y, z)];
         if ((cd & CODE_SELF) && (cd & CODE_SY0)) {
-            const float d = smoke[c];
+            const float d = smoke[cell_index(g, x, y, z)];
             const float t = __fmaf_rn(__fmul_rn(d, gravity), dt, __fmul_rn(__fmul_rn(d, alpha), dt));
             vv = __fadd_rn(t, vv);
             dirty = true;
@@ -149,28 +152,57 @@ __device__ __forceinline__ float pressure_p(float u0, float u1, float v0, float 
     return __double2float_rn(__dmul_rn((double)q, -1.9));
 }
 
+// Branch-free variant used by the hot kernels.  div/acc with acc in {1..6} is computed as
+//   r = RN(1/acc) (table), q0 = RN(div*r), rem = fma(-q0, acc, div) (exact), q = fma(rem, r, q0)
+// which equals the IEEE quotient for EVERY finite div with biased exponent >= 2 (checked exhaustively on all
+// 2^32 inputs for acc = 1..6; the only misses are denormal-range inputs with acc = 6).  `slow` is set for the
+// inputs outside that proven range (tiny non-zero, huge, inf, nan); the caller then recomputes that cell with
+// pressure_p().  (Non-finite divergence is not flagged: inf/nan fields have no defined parity.)  This removes
+// MUFU.RCP and the FCHK/CALL slow-path structure from the inner loop so that the compiler can interleave
+// independent cell updates.
+__constant__ float c_rcp[8] = {0.0f, 1.0f, 0.5f, 0x1.555556p-2f, 0.25f, 0x1.99999ap-3f, 0x1.555556p-3f, 0.0f};
+
+__device__ __forceinline__ float pressure_p_fast(float u0, float u1, float v0, float v1, float w0, float w1, int acc,
+                                                 bool& slow)
+{
+    float div = __fadd_rn(-u0, u1);
+    div = __fadd_rn(div, -v0);
+    div = __fadd_rn(div, v1);
+    div = __fadd_rn(div, -w0);
+    div = __fadd_rn(div, w1);
+    const float r = c_rcp[acc];
+    const float q0 = __fmul_rn(div, r);
+    const float rem = __fmaf_rn(-q0, (float)acc, div);
+    const float q = __fmaf_rn(rem, r, q0);
+    // the proven-exact range is |div| >= 2^-125; a quotient below FLT_MIN can only come from below that range
+    slow = (fabsf(q) < 1.17549435e-38f) && (div != 0.0f);
+    return __double2float_rn(__dmul_rn((double)q, -1.9));
+}
+
 // One red or black half-sweep, in place (cu:356-394; schedule cu:797-801).
 // offset 0 <-> (x+y+z) even, 1 <-> odd.  One thread per PAIR of x-adjacent cells: exactly one cell of
 // the pair has the active colour, so a warp covers 64 consecutive cells of a row and every lane works.
-// Same-colour cells share no face => race-free in place.
+// Same-colour cells share no face => race-free in place.  Block = 64 pairs x 4 rows; grid.z walks planes.
+// The stencil code and the six faces are loaded together (independent loads, one DRAM latency), the
+// activity test comes after.
 __global__ void __launch_bounds__(256) k_pressure_half(GridP g, float* __restrict__ u, float* __restrict__ v,
                                                        float* __restrict__ w, const unsigned char* __restrict__ code,
                                                        int offset, int za)
 {
-    const int halfW = (g.W + 1) >> 1;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= halfW * g.H) return;
-    const int y = i / halfW, xp = i - y * halfW;
-    const int z = za + blockIdx.y;
+    const int xp = blockIdx.x * 64 + threadIdx.x;
+    const int y = blockIdx.y * 4 + threadIdx.y;
+    const int z = za + blockIdx.z;
     const int x = 2 * xp + ((y + z + offset) & 1);
-    if (x >= g.W) return;
-    const unsigned cd = code[cell_index(g, x, y, z)];
-    if (!(cd & CODE_ACTIVE)) return;
-    const int acc = __popc(cd & 63u);
+    if (x < 1 || y < 1 || x >= g.W - 1 || y >= g.H - 1) return; // interior cells only (z range set by the launch)
     const long long n = node_index(g, x, y, z);
     const long long nx = n + 1, ny = n + g.P, nz = n + g.nplane;
+    const unsigned cd = code[code_index(g, x, y, z)];
     const float u0 = u[n], u1 = u[nx], v0 = v[n], v1 = v[ny], w0 = w[n], w1 = w[nz];
-    const float p = pressure_p(u0, u1, v0, v1, w0, w1, acc);
+    if (!(cd & CODE_ACTIVE)) return;
+    const int acc = __popc(cd & 63u);
+    bool slow;
+    float p = pressure_p_fast(u0, u1, v0, v1, w0, w1, acc, slow);
+    if (slow) p = pressure_p(u0, u1, v0, v1, w0, w1, acc);
     if (cd & CODE_SX0) u[n] = __fsub_rn(u0, p);
     if (cd & CODE_SX1) u[nx] = __fadd_rn(u1, p);
     if (cd & CODE_SY0) v[n] = __fsub_rn(v0, p);
@@ -289,7 +321,7 @@ __global__ void __launch_bounds__(256) k_advect_velocity(GridP g, const float* _
     const int y = i / g.P, x = i - y * g.P;
     const int z = za + blockIdx.y;
     if (x < 1 || y < 1 || z < 1 || x >= g.W || y >= g.H || z >= g.D) return;
-    const unsigned cd = code[cell_index(g, x, y, z)];
+    const unsigned cd = code[code_index(g, x, y, z)];
     if (!(cd & CODE_SELF)) return;
     const bool doU = (cd & CODE_SX0) && y < g.H - 1 && z < g.D - 1;
     const bool doV = (cd & CODE_SY0) && x < g.W - 1 && z < g.D - 1;
@@ -338,7 +370,7 @@ __global__ void __launch_bounds__(256) k_advect_smoke(GridP g, const float* __re
     const int z = za + blockIdx.y;
     if (x < 1 || y < 1 || z < 1 || x >= g.W - 1 || y >= g.H - 1 || z >= g.D - 1) return;
     const long long c = cell_index(g, x, y, z);
-    if (!(code[c] & CODE_SELF)) return;
+    if (!(code[code_index(g, x, y, z)] & CODE_SELF)) return;
     const long long n = node_index(g, x, y, z);
     const float mu = __fmul_rn(__fmul_rn(__fadd_rn(u[n], u[n + 1]), -0.5f), dt);
     const float mv = __fmul_rn(__fmul_rn(__fadd_rn(v[n], v[n + g.P]), -0.5f), dt);
@@ -363,7 +395,7 @@ __global__ void __launch_bounds__(256) k_max_divergence(GridP g, const float* __
         const int y = i / g.W, x = i - y * g.W;
         const int z = za + blockIdx.y;
         if (x >= 1 && y >= 1 && z >= 1 && x < g.W - 1 && y < g.H - 1 && z < g.D - 1 &&
-            (code[cell_index(g, x, y, z)] & CODE_SELF)) {
+            (code[code_index(g, x, y, z)] & CODE_SELF)) {
             const long long n = node_index(g, x, y, z);
             float div = __fadd_rn(-u[n], u[n + 1]);
             div = __fadd_rn(div, -v[n]);

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -16,6 +18,7 @@
 #include "../../include/smoke_b200.h"
 #include "grid.h"
 #include "kernels_basic.cuh"
+#include "kernels_pressure_fused.cuh"
 
 namespace {
 
@@ -41,8 +44,10 @@ struct smk_sim {
     float* u[2]{};
     float* v[2]{};
     float* w[2]{};
+    float* scratch[3]{}; // second u,v,w set for the out-of-place fused pressure passes (lazy)
     unsigned char* mask = nullptr;
     unsigned char* code = nullptr;
+    int num_sms = 148;
     unsigned* d_scalar = nullptr; // device scratch for reductions
 
     int now = 1, past = 0; // indexNow / tempIndexPast, cu:707-708
@@ -92,6 +97,7 @@ int fail(smk_sim* s, int code, const std::string& msg)
 
 size_t node_count(const GridP& g) { return (size_t)g.nplane * g.nzn; }
 size_t cell_count(const GridP& g) { return (size_t)g.cplane * g.nzc; }
+size_t code_count(const GridP& g) { return (size_t)g.kplane * g.nzc; }
 
 cudaEvent_t get_event(smk_sim* s)
 {
@@ -198,26 +204,106 @@ void pressure_planes(const GridP& g, int& za, int& zb)
     zb = std::min(g.D - 1, g.zlo + g.nzc);
 }
 
-int launch_halfsweep(smk_sim* s, int offset)
+int launch_halfsweep(smk_sim* s, int offset, int zlo_req = INT32_MIN, int zhi_req = INT32_MAX)
 {
     const GridP& g = s->g;
     int za, zb;
     pressure_planes(g, za, zb);
+    za = std::max(za, zlo_req);
+    zb = std::min(zb, zhi_req);
     if (zb <= za) return SMK_OK;
     const int n = s->now;
-    const long long pairs = (long long)((g.W + 1) >> 1) * g.H;
-    smk::k_pressure_half<<<row_grid(pairs, zb - za), 256, 0, s->stream>>>(g, s->u[n], s->v[n], s->w[n], s->code, offset, za);
+    const int halfW = (g.W + 1) >> 1;
+    const dim3 grid((unsigned)((halfW + 63) / 64), (unsigned)((g.H + 3) / 4), (unsigned)(zb - za));
+    smk::k_pressure_half<<<grid, dim3(64, 4, 1), 0, s->stream>>>(g, s->u[n], s->v[n], s->w[n], s->code, offset, za);
     count_launch(s, SMK_STAGE_PRESSURE);
     return SMK_OK;
+}
+
+// ---- fused pressure passes (kernels_pressure_fused.cuh) ---------------------------------------------------
+template <int K, int FUSED_NW, int FUSED_RPW>
+int launch_fused_pass_cfg(smk_sim* s, int sweep0)
+{
+    using C = smk::FusedCfg<K, FUSED_NW, FUSED_RPW>;
+    const GridP& g = s->g;
+    static bool configured = false;
+    auto kern = smk::k_pressure_fused<K, FUSED_NW, FUSED_RPW>;
+    if (!configured) {
+        CK(s, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        configured = true;
+    }
+    if (!s->scratch[0]) {
+        const size_t nb = node_count(g) * sizeof(float);
+        for (int i = 0; i < 3; i++) {
+            CK(s, cudaMalloc(&s->scratch[i], nb));
+            CK(s, cudaMemsetAsync(s->scratch[i], 0, nb, s->stream));
+        }
+    }
+    const int tx = (g.W + 1 + C::OX - 1) / C::OX, ty = (g.SY + C::OY - 1) / C::OY;
+    // z-chunking: enough CTAs to fill the SMs, as few lead-in/lead-out planes (2K per chunk) as possible
+    int best_n = 1;
+    double best = -1.0;
+    for (int n = 1; n <= std::max(1, g.nzn / 4); n++) {
+        const int zc = (g.nzn + n - 1) / n;
+        const long ctas = (long)tx * ty * ((g.nzn + zc - 1) / zc);
+        const long waves = (ctas + s->num_sms - 1) / s->num_sms;
+        const double eff = (double)ctas / (double)(waves * s->num_sms) * (double)zc / (double)(zc + 2 * K);
+        if (eff > best + 1e-9) { best = eff; best_n = n; }
+    }
+    const int zchunk = (g.nzn + best_n - 1) / best_n;
+    const dim3 grid((unsigned)tx, (unsigned)ty, (unsigned)((g.nzn + zchunk - 1) / zchunk));
+    const int n = s->now;
+    kern<<<grid, C::THREADS, C::SMEM, s->stream>>>(g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2],
+                                                    s->code, sweep0, zchunk);
+    std::swap(s->u[n], s->scratch[0]);
+    std::swap(s->v[n], s->scratch[1]);
+    std::swap(s->w[n], s->scratch[2]);
+    count_launch(s, SMK_STAGE_PRESSURE);
+    return SMK_OK;
+}
+
+template <int K>
+int launch_fused_pass(smk_sim* s, int sweep0)
+{
+    // tile shape (warps x rows per warp); tuning knob SMK_FUSED_CFG for experiments, default 24x2
+    static const int cfg = getenv("SMK_FUSED_CFG") ? atoi(getenv("SMK_FUSED_CFG")) : 242;
+    switch (cfg) {
+    case 163: return launch_fused_pass_cfg<K, 16, 3>(s, sweep0);
+    case 124: return launch_fused_pass_cfg<K, 12, 4>(s, sweep0);
+    case 321: return launch_fused_pass_cfg<K, 32, 1>(s, sweep0);
+    case 162: return launch_fused_pass_cfg<K, 16, 2>(s, sweep0);
+    default: return launch_fused_pass_cfg<K, 24, 2>(s, sweep0);
+    }
 }
 
 int stage_pressure(smk_sim* s)
 {
     Span sp(s, SMK_STAGE_PRESSURE);
-    for (int i = 0; i < s->iterations; i++) {
-        launch_halfsweep(s, 0);
-        launch_halfsweep(s, 1);
+    const int total = 2 * s->iterations; // half-sweeps, alternating offset 0,1 (cu:797-801)
+    int fuse = s->fuse;
+    if (fuse == 0) fuse = (s->g.W + 1 < 32 || s->g.nzn < 8) ? 1 : 4; // tiny grids: tiles would be mostly halo
+    int done = 0, rc = SMK_OK;
+    // EXPERIMENT (env SMK_L2_ZC / SMK_L2_G): L2-resident wavefront of the unfused kernel.  Groups of G
+    // half-sweeps are applied chunk by chunk (Zc planes), sweep j shifted down by j planes, so the planes
+    // a group touches stay in the 126 MB L2 between launches.  Same per-cell order of updates => same bits.
+    static const int l2_zc = getenv("SMK_L2_ZC") ? atoi(getenv("SMK_L2_ZC")) : 0;
+    static const int l2_g = getenv("SMK_L2_G") ? atoi(getenv("SMK_L2_G")) : 20;
+    if (fuse == 1 && l2_zc > 0) {
+        const GridP& g = s->g;
+        while (done < total) {
+            const int G = std::min(l2_g, total - done);
+            for (int c0 = 0; c0 - G < g.D; c0 += l2_zc)
+                for (int j = 0; j < G; j++) launch_halfsweep(s, (done + j) & 1, c0 - j, c0 + l2_zc - j);
+            done += G;
+        }
     }
+    while (done < total && rc == SMK_OK) {
+        const int left = total - done;
+        if (fuse >= 4 && left >= 4 && (done & 1) == 0) { rc = launch_fused_pass<4>(s, done); done += 4; }
+        else if (fuse >= 2 && left >= 2 && (done & 1) == 0) { rc = launch_fused_pass<2>(s, done); done += 2; }
+        else { rc = launch_halfsweep(s, done & 1); done += 1; }
+    }
+    if (rc) return rc;
     CK(s, cudaGetLastError());
     return SMK_OK;
 }
@@ -368,6 +454,10 @@ int create_common(smk_sim** out, unsigned W, unsigned H, unsigned D, int c0, int
     const int zhc = std::min((int)D, c1 + ghost);
     g.nzc = zhc - g.zlo;
     g.nzn = g.nzc + 1;
+    g.PC = (int)((W + 15) / 16 * 16);
+    g.kplane = (long long)g.PC * g.H;
+    cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (s->num_sms <= 0) s->num_sms = 148;
 
 #define CKN(call)                                                                                       \
     do {                                                                                                \
@@ -392,9 +482,9 @@ int create_common(smk_sim** out, unsigned W, unsigned H, unsigned D, int c0, int
         CKN(cudaMemsetAsync(s->w[i], 0, nb, s->stream));
     }
     CKN(cudaMalloc(&s->mask, cell_count(g)));
-    CKN(cudaMalloc(&s->code, cell_count(g)));
+    CKN(cudaMalloc(&s->code, code_count(g)));
     CKN(cudaMalloc(&s->d_scalar, 64));
-    CKN(cudaMemsetAsync(s->code, 0, cell_count(g), s->stream));
+    CKN(cudaMemsetAsync(s->code, 0, code_count(g), s->stream));
     // mask: fluid everywhere, solid on the plane y == 0 (cu:200-207)
     CKN(cudaMemsetAsync(s->mask, 1, cell_count(g), s->stream));
     CKN(cudaMemset2DAsync(s->mask, (size_t)g.cplane, 0, (size_t)g.W, (size_t)g.nzc, s->stream));
@@ -436,6 +526,7 @@ int smk_destroy(smk_sim* s)
     for (int i = 0; i < 2; i++) {
         cudaFree(s->smoke[i]); cudaFree(s->u[i]); cudaFree(s->v[i]); cudaFree(s->w[i]);
     }
+    for (int i = 0; i < 3; i++) cudaFree(s->scratch[i]);
     cudaFree(s->mask); cudaFree(s->code); cudaFree(s->d_scalar);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     cudaGetLastError();
@@ -497,6 +588,7 @@ int smk_set_solver(smk_sim* s, int variant, int iterations, int fuse)
 {
     if (!s || iterations < 0 || fuse < 0) return SMK_ERR_ARG;
     if (variant != SMK_SOLVER_RBGS) return fail(s, SMK_ERR_ARG, "solver variant not available");
+    if (fuse != 0 && fuse != 1 && fuse != 2 && fuse != 4) return fail(s, SMK_ERR_ARG, "fuse must be 0, 1, 2 or 4");
     s->solver = variant; s->iterations = iterations; s->fuse = fuse;
     return SMK_OK;
 }

@@ -205,3 +205,33 @@ def test_c2_256_one_tick_property_checks(po, smk):
     u = a.get_field(po.U, po.NOW)
     assert np.abs(u[:, :, 0]).max() == 0.0 and np.abs(u[:, :, -1]).max() == 0.0 and np.abs(u[0]).max() == 0.0
     a.close()
+
+
+@pytest.mark.parametrize("fuse", [1, 2, 4])
+@pytest.mark.parametrize("dims", [(20, 18, 16), (120, 50, 40), (57, 41, 9), (130, 100, 70)])
+def test_fused_pressure_passes_identical(po, smk, dims, fuse):
+    """Temporal blocking only reorders WHICH cell is updated WHEN, never the data dependencies of the
+    red/black sweeps: K fused half-sweeps per launch must give the same bits as K launches (and as the
+    oracle).  Sizes straddle several 56x40 output tiles and z-chunks; random mask and fields."""
+    W, H, D = dims
+    st = random_state(po, W, H, D, seed=3)
+    scene = (W, H, D, -9.82, 3.0, [], [])
+    a, b = make_pair(po, smk, scene, st)
+    a.set_solver(0, 7, fuse)   # 14 half-sweeps: 3 passes of 4 + one of 2 (fuse=4), 7 of 2 (fuse=2)
+    a.flip(); b.flip(); a.fill(); b.fill()
+    a.pressure()
+    for i in range(7):
+        b.pressure_halfsweep(0); b.pressure_halfsweep(1)
+    compare(po, a, b, f"{dims} fuse={fuse}")
+    a.close()
+
+
+def test_fused_full_steps_c1_obstacle(po, smk):
+    """C1 (80^3, obstacle) for 5 ticks with the default fused schedule (15 passes of 4) vs the oracle."""
+    sc = po.SCENES["C1"]
+    a, b = make_pair(po, smk, sc)
+    a.set_solver(0, 30, 4)
+    for t in range(5):
+        a.step(po.tick_dt(t)); b.step(po.tick_dt(t))
+    compare(po, a, b, "C1 fused x4")
+    a.close()
