@@ -179,6 +179,19 @@ __device__ __forceinline__ float pressure_p_fast(float u0, float u1, float v0, f
     return __double2float_rn(__dmul_rn((double)q, -1.9));
 }
 
+// Exact d / 6 for 0 < |d| < 2^-125 (biased exponent 0 or 1), the only inputs for which the reciprocal-plus-
+// correction sequence can miss (a tie on the denormal grid).  In that range the bit pattern of |d| IS the value in
+// units of 2^-149 (the denormal encoding continues into the first normal binade), the quotient is below 2^23 units,
+// so IEEE round-to-nearest-even is plain integer arithmetic: m = 6k + r  ->  k + (r > 3 || (r == 3 && k odd)).
+__device__ __forceinline__ float div6_tiny(float d)
+{
+    const unsigned b = __float_as_uint(d), m = b & 0x7fffffffu;
+    const unsigned k = __umulhi(m, 0xAAAAAAABu) >> 2; // m / 6
+    const unsigned r = m - 6u * k;
+    const unsigned q = k + ((r > 3u || (r == 3u && (k & 1u))) ? 1u : 0u);
+    return __uint_as_float(q | (b & 0x80000000u));
+}
+
 // One red or black half-sweep, in place (cu:356-394; schedule cu:797-801).
 // offset 0 <-> (x+y+z) even, 1 <-> odd.  One thread per PAIR of x-adjacent cells: exactly one cell of
 // the pair has the active colour, so a warp covers 64 consecutive cells of a row and every lane works.

@@ -98,6 +98,16 @@ k_pressure_fused(GridP g, const float* __restrict__ ui, const float* __restrict_
         }
     };
 
+    // per-thread, per-row constants of the sweep phases
+    int dv1[RPW], rowpar[RPW];
+#pragma unroll
+    for (int r = 0; r < RPW; r++) {
+        const int yl = wid + r * NW;
+        dv1[r] = yl < LY - 1 ? LX : 0;                       // last tile row is never updated: keep v1's address legal
+        rowpar[r] = (y0 + yl + sweep0 + 1) & 1;              // + t gives the x parity of the active colour
+    }
+    const float2 M1 = make_float2(-1.0f, -1.0f);
+
     prefetch(t0);
     int slot_t = 0; // ring slot of plane t
     for (int t = t0; t <= t1; t++) {
@@ -113,57 +123,107 @@ k_pressure_fused(GridP g, const float* __restrict__ ui, const float* __restrict_
         if (t < t1) prefetch(t + 1); // in flight during the sweeps
         __syncthreads();
 
+        // Sweep j runs on cell plane c = t-j with colour (sweep0+j-1)&1, so the x parity of the active cell of a
+        // row, (y + c + sweep0 + j - 1) & 1 = (y + t + sweep0 + 1) & 1, is the same for all K sweeps of this step.
+        int base[RPW], du1[RPW];
+        unsigned sh[RPW], msk[RPW];
+#pragma unroll
+        for (int r = 0; r < RPW; r++) {
+            const int par = (rowpar[r] + t) & 1;
+            const bool edge = par && lane == 31;                 // cell 63 of the row: u[64] is not in the tile
+            base[r] = srow[r] + par * 32;
+            du1[r] = edge ? 0 : (par ? -31 : 32);                // O[i] -> E[i+1],  E[i] -> O[i]
+            sh[r] = par * 8;
+            msk[r] = (edge || dv1[r] == 0) ? 0u : 0xffu;
+        }
+
 #pragma unroll
         for (int j = 1; j <= K; j++) {
-            const int c = t - j; // cell plane of sweep j
-            if (c >= t0) {
+            if (t - j >= t0) { // cell plane c = t-j is in the ring
                 int sl = slot_t - j; if (sl < 0) sl += R;          // slot of plane c
                 int sl1 = sl + 1; if (sl1 == R) sl1 = 0;           // slot of plane c+1
-                const int par0 = (y0 + c + sweep0 + j - 1) & 1;    // x parity of the active colour in row yl = 0
-                int a[RPW], a_u1[RPW], a_v1[RPW], a_w1[RPW];
+                const int so = sl * PL, so1 = sl1 * PL, sk = sl * (PL / 2);
+                int a[RPW];
                 unsigned cd[RPW];
-                float u0[RPW], u1[RPW], v0[RPW], v1[RPW], w0[RPW], w1[RPW], p[RPW];
-                bool slow[RPW];
-#pragma unroll
-                for (int r = 0; r < RPW; r++) {
-                    const int yl = wid + r * NW;
-                    const int par = (par0 + yl) & 1;
-                    const bool edge = par && lane == 31;           // cell 63 of the row: u[64] is not in the tile
-                    a[r] = sl * PL + srow[r] + par * 32;
-                    a_u1[r] = edge ? a[r] : a[r] + (par ? -31 : 32); // O[i] -> E[i+1],  E[i] -> O[i]
-                    a_v1[r] = a[r] + (yl < LY - 1 ? LX : 0);       // last row: never updated, keep the address legal
-                    a_w1[r] = a[r] + (sl1 - sl) * PL;
-                    const unsigned cw = sc[sl * (PL / 2) + yl * 32 + lane];
-                    cd[r] = (cw >> (par * 8)) & 0xffu;
-                    if (!(cd[r] & CODE_ACTIVE) || yl == LY - 1 || edge) cd[r] = 0;
-                    u0[r] = su[a[r]]; u1[r] = su[a_u1[r]];
-                    v0[r] = sv[a[r]]; v1[r] = sv[a_v1[r]];
-                    w0[r] = sw[a[r]]; w1[r] = sw[a_w1[r]];
-                }
+                float u0[RPW], u1[RPW], v0[RPW], v1[RPW], w0[RPW], w1[RPW], p[RPW], rr[RPW], af[RPW], dv[RPW];
                 bool any_slow = false;
 #pragma unroll
                 for (int r = 0; r < RPW; r++) {
-                    p[r] = pressure_p_fast(u0[r], u1[r], v0[r], v1[r], w0[r], w1[r], __popc(cd[r] & 63u), slow[r]);
-                    slow[r] = slow[r] && cd[r] != 0;
-                    any_slow |= slow[r];
+                    a[r] = so + base[r];
+                    const unsigned cw = sc[sk + (wid + r * NW) * 32 + lane];
+                    cd[r] = (cw >> sh[r]) & msk[r];
+                    if (!(cd[r] & CODE_ACTIVE)) cd[r] = 0;
+                    u0[r] = su[a[r]]; u1[r] = su[a[r] + du1[r]];
+                    v0[r] = sv[a[r]]; v1[r] = sv[a[r] + dv1[r]];
+                    w0[r] = sw[a[r]]; w1[r] = sw[so1 + base[r]];
+                    const int acc = __popc(cd[r] & 63u);
+                    rr[r] = c_rcp[acc];
+                    af[r] = -(float)acc;
                 }
-                if (__any_sync(0xffffffffu, any_slow)) { // denormal-range divergence: exact IEEE division
+                // pressure_p_fast() on pairs of rows with packed f32x2 instructions (same roundings per lane:
+                // x*(-1)+y == y-x exactly rounded once, like the scalar FADDs)
+#pragma unroll
+                for (int r = 0; r + 1 < RPW; r += 2) {
+                    float2 d = __ffma2_rn(make_float2(u0[r], u0[r + 1]), M1, make_float2(u1[r], u1[r + 1]));
+                    d = __ffma2_rn(make_float2(v0[r], v0[r + 1]), M1, d);
+                    d = __fadd2_rn(d, make_float2(v1[r], v1[r + 1]));
+                    d = __ffma2_rn(make_float2(w0[r], w0[r + 1]), M1, d);
+                    d = __fadd2_rn(d, make_float2(w1[r], w1[r + 1]));
+                    const float2 R2 = make_float2(rr[r], rr[r + 1]);
+                    const float2 q0 = __fmul2_rn(d, R2);
+                    const float2 rem = __ffma2_rn(q0, make_float2(af[r], af[r + 1]), d);
+                    const float2 q = __ffma2_rn(rem, R2, q0);
+                    dv[r] = d.x; dv[r + 1] = d.y;
+                    p[r] = __double2float_rn(__dmul_rn((double)q.x, -1.9));
+                    p[r + 1] = __double2float_rn(__dmul_rn((double)q.y, -1.9));
+                    any_slow |= (fabsf(q.x) < 1.17549435e-38f && d.x != 0.0f && cd[r] != 0) ||
+                                (fabsf(q.y) < 1.17549435e-38f && d.y != 0.0f && cd[r + 1] != 0);
+                }
+                if (RPW & 1) {
+                    constexpr int r = RPW - 1;
+                    bool slow;
+                    p[r] = pressure_p_fast(u0[r], u1[r], v0[r], v1[r], w0[r], w1[r], __popc(cd[r] & 63u), slow);
+                    dv[r] = 1.0f;
+                    any_slow |= slow && cd[r] != 0;
+                }
+                if (__any_sync(0xffffffffu, any_slow)) { // denormal-range divergence somewhere: exact IEEE division
 #pragma unroll
                     for (int r = 0; r < RPW; r++)
-                        if (slow[r]) p[r] = pressure_p(u0[r], u1[r], v0[r], v1[r], w0[r], w1[r], __popc(cd[r] & 63u));
+                        if (cd[r]) p[r] = pressure_p(u0[r], u1[r], v0[r], v1[r], w0[r], w1[r], __popc(cd[r] & 63u));
+                }
+#pragma unroll
+                for (int r = 0; r + 1 < RPW; r += 2) {
+                    const float2 P2 = make_float2(p[r], p[r + 1]);
+                    const float2 nu0 = __ffma2_rn(P2, M1, make_float2(u0[r], u0[r + 1]));
+                    const float2 nu1 = __fadd2_rn(make_float2(u1[r], u1[r + 1]), P2);
+                    const float2 nv0 = __ffma2_rn(P2, M1, make_float2(v0[r], v0[r + 1]));
+                    const float2 nv1 = __fadd2_rn(make_float2(v1[r], v1[r + 1]), P2);
+                    const float2 nw0 = __ffma2_rn(P2, M1, make_float2(w0[r], w0[r + 1]));
+                    const float2 nw1 = __fadd2_rn(make_float2(w1[r], w1[r + 1]), P2);
+                    u0[r] = nu0.x; u0[r + 1] = nu0.y; u1[r] = nu1.x; u1[r + 1] = nu1.y;
+                    v0[r] = nv0.x; v0[r + 1] = nv0.y; v1[r] = nv1.x; v1[r + 1] = nv1.y;
+                    w0[r] = nw0.x; w0[r + 1] = nw0.y; w1[r] = nw1.x; w1[r + 1] = nw1.y;
+                }
+                if (RPW & 1) {
+                    constexpr int r = RPW - 1;
+                    u0[r] = __fsub_rn(u0[r], p[r]); u1[r] = __fadd_rn(u1[r], p[r]);
+                    v0[r] = __fsub_rn(v0[r], p[r]); v1[r] = __fadd_rn(v1[r], p[r]);
+                    w0[r] = __fsub_rn(w0[r], p[r]); w1[r] = __fadd_rn(w1[r], p[r]);
                 }
 #pragma unroll
                 for (int r = 0; r < RPW; r++) {
-                    if (cd[r] & CODE_SX0) su[a[r]] = __fsub_rn(u0[r], p[r]);
-                    if (cd[r] & CODE_SX1) su[a_u1[r]] = __fadd_rn(u1[r], p[r]);
-                    if (cd[r] & CODE_SY0) sv[a[r]] = __fsub_rn(v0[r], p[r]);
-                    if (cd[r] & CODE_SY1) sv[a_v1[r]] = __fadd_rn(v1[r], p[r]);
-                    if (cd[r] & CODE_SZ0) sw[a[r]] = __fsub_rn(w0[r], p[r]);
-                    if (cd[r] & CODE_SZ1) sw[a_w1[r]] = __fadd_rn(w1[r], p[r]);
+                    if (cd[r] & CODE_SX0) su[a[r]] = u0[r];
+                    if (cd[r] & CODE_SX1) su[a[r] + du1[r]] = u1[r];
+                    if (cd[r] & CODE_SY0) sv[a[r]] = v0[r];
+                    if (cd[r] & CODE_SY1) sv[a[r] + dv1[r]] = v1[r];
+                    if (cd[r] & CODE_SZ0) sw[a[r]] = w0[r];
+                    if (cd[r] & CODE_SZ1) sw[so1 + base[r]] = w1[r];
                 }
             }
-            __syncthreads();
+            // no barrier between the sweeps of one step: see kernels_pressure_quad.cuh (the only shared face of
+            // consecutive sweeps is w[t-j] of the thread's own column)
         }
+        __syncthreads();
 
         // node plane t-K is final: ring -> output buffers (interior of the tile only)
         const int s = t - K;

@@ -1,0 +1,257 @@
+// kernels_pressure_reg.cuh -- temporally blocked pressure kernel, register-resident columns (the default).
+//
+// Same schedule and the same proof of bit-identity as kernels_pressure_fused.cuh (K half-sweeps per launch while
+// marching an (x,y) tile along z; trapezoid halo; out of place).  What changed is WHERE the ring of K+1 planes
+// lives.  Measurements of the all-shared-memory versions (profiles/r1_fused_smem_ablation.txt) showed ~116 B of
+// shared-memory traffic per cell update and the block barriers of every z-step dominating the time, far from both
+// the HBM and the issue limits.  Observation: with a lane owning a QUAD of x-consecutive cells of one row,
+//
+//   * the w faces of a cell column are touched by that column only            -> registers, never shared
+//   * the u faces u[4h+1..4h+3] are interior to the quad, u[4h] is written only by the lane to the left
+//     (and only in odd-parity steps)                                          -> registers + one shuffle pair
+//   * only the v faces are shared between rows (different half-warps / warps) -> shared memory
+//
+// so a sweep phase costs four 64-bit shared-memory accesses instead of fifteen, and -- because consecutive sweeps
+// of one z-step touch different planes except for the w face of the thread's own column -- the K sweeps of a step
+// need no barrier between them.  One __syncthreads per z-step remains (v faces cross rows between steps).
+//
+// Register ring: UE/UO/WE/WO[k] hold plane t-k (k = 0..K) as float2 pairs split by x parity, E = (f[4h], f[4h+2]),
+// O = (f[4h+1], f[4h+3]); the pairs feed the packed f32x2 arithmetic directly.  The ring is shifted by register moves
+// once per step (static indices only, no local memory).
+#pragma once
+#include <cuda_runtime.h>
+#include "grid.h"
+#include "kernels_basic.cuh"
+
+namespace smk {
+
+template <int K, int NW>
+struct RegCfg {
+    static constexpr int LX = 64;              // loaded tile width in cells (one half-warp = one row of 16 quads)
+    static constexpr int LY = 2 * NW;          // loaded tile height
+    static constexpr int RS = 68;              // floats per shared v row: E[0..33] | O[0..33]
+    static constexpr int HO = 34;
+    static constexpr int R = K + 1;            // ring depth
+    static constexpr int PLS = (LY + 1) * RS;  // floats per shared v plane (one dummy row)
+    static constexpr int OX = LX - 2 * K, OY = LY - 2 * K;
+    static constexpr int THREADS = NW * 32;
+    static constexpr size_t SMEM = (size_t)R * PLS * sizeof(float);
+};
+
+// exact q = d / acc for the neighbour counts 1..6 (see pressure_p_fast); returns true if any lane needs the
+// IEEE fallback (denormal-range d with acc = 6 is the only inexact case)
+__device__ __forceinline__ float2 p_pair_from_q(float2 q)
+{
+    return make_float2(__double2float_rn(__dmul_rn((double)q.x, -1.9)), __double2float_rn(__dmul_rn((double)q.y, -1.9)));
+}
+
+// One sweep phase of one lane on ring position J (plane t-J): two same-colour cells of the lane's quad.
+// PAR = x parity of the active colour (warp uniform).  ue/uo/we/wo = the register ring, sv = shared v plane.
+template <int PAR, int RS, int HO>
+__device__ __forceinline__ void reg_update(float2& ue, float2& uo, float2& we, float2& wo, float2& we1, float2& wo1,
+                                           float* __restrict__ sv, int vrow, unsigned cw, int h)
+{
+    const float2 M1 = make_float2(-1.0f, -1.0f);
+    float2 U0, U1, W0, W1;
+    if (PAR == 0) { U0 = ue; U1 = uo; W0 = we; W1 = we1; }
+    else {
+        U0 = uo; W0 = wo; W1 = wo1;
+        U1 = make_float2(ue.y, __shfl_down_sync(0xffffffffu, ue.x, 1)); // u[4h+2], u[4h+4] (next quad's first face)
+    }
+    float* pv = sv + vrow + PAR * HO;
+    float2 V0 = *reinterpret_cast<float2*>(pv), V1 = *reinterpret_cast<float2*>(pv + RS);
+    const unsigned cs = cw >> (PAR * 8); // byte 0 = code of cell A, byte 2 = code of cell B
+
+    float2 d = __ffma2_rn(U0, M1, U1);   // -u0 + u1           (cu:379-381, left to right, one rounding each)
+    d = __ffma2_rn(V0, M1, d);           //  ... - v0
+    d = __fadd2_rn(d, V1);               //  ... + v1
+    d = __ffma2_rn(W0, M1, d);           //  ... - w0
+    d = __fadd2_rn(d, W1);               //  ... + w1
+
+    // Fast path: every cell of the warp is either "open" (code 0xff: fluid, six fluid neighbours, acc = 6, every
+    // face updated) or not updated at all (no ACTIVE bit: solid, domain boundary, outside the domain / slab).
+    // Only cells next to a solid cell need the general path below.
+    const unsigned actm = cs & 0x00400040u;                          // ACTIVE bits of cells A and B
+    const unsigned want = (actm << 2) - (actm >> 6);                 // 0xff in the byte of every ACTIVE cell
+    const bool simple = ((cs & 0x00ff00ffu) & want) == want;         // ACTIVE => code == 0xff
+    if (__all_sync(0xffffffffu, simple)) {
+        const float r6 = 0x1.555556p-3f; // RN(1/6)
+        const float2 q0 = __fmul2_rn(d, make_float2(r6, r6));
+        const float2 rem = __ffma2_rn(q0, make_float2(-6.0f, -6.0f), d);
+        const float2 q = __ffma2_rn(rem, make_float2(r6, r6), q0);
+        float2 P = p_pair_from_q(q);
+        // the correction sequence is exact for every |d| >= 2^-125 (exhaustive check); below that (and d != 0)
+        // a tie on the denormal grid can round the wrong way -> IEEE division for those lanes
+        const unsigned ax = __float_as_uint(d.x) & 0x7fffffffu, ay = __float_as_uint(d.y) & 0x7fffffffu;
+        const bool sx = (ax - 1u < 0x00ffffffu) && (actm & 0x40u), sy = (ay - 1u < 0x00ffffffu) && (actm & 0x400000u);
+        if (__any_sync(0xffffffffu, sx || sy)) {
+            if (sx) P.x = __double2float_rn(__dmul_rn((double)div6_tiny(d.x), -1.9));
+            if (sy) P.y = __double2float_rn(__dmul_rn((double)div6_tiny(d.y), -1.9));
+        }
+        if (!(actm & 0x40u)) P.x = 0.f;      // cells that are not updated: old -/+ 0 = old
+        if (!(actm & 0x400000u)) P.y = 0.f;
+        U0 = __ffma2_rn(P, M1, U0); U1 = __fadd2_rn(U1, P);
+        V0 = __ffma2_rn(P, M1, V0); V1 = __fadd2_rn(V1, P);
+        W0 = __ffma2_rn(P, M1, W0); W1 = __fadd2_rn(W1, P);
+    } else {
+        // general path: per-cell neighbour count, per-face masks (a masked face gets its old value back)
+        unsigned cA = cs & 0xffu, cB = (cs >> 16) & 0xffu;
+        if (!(cA & CODE_ACTIVE)) cA = 0;
+        if (!(cB & CODE_ACTIVE)) cB = 0;
+        const int nA = __popc(cA & 63u), nB = __popc(cB & 63u);
+        const float2 rr = make_float2(c_rcp[nA], c_rcp[nB]);
+        const float2 q0 = __fmul2_rn(d, rr);
+        const float2 rem = __ffma2_rn(q0, make_float2(-(float)nA, -(float)nB), d);
+        const float2 q = __ffma2_rn(rem, rr, q0);
+        float2 P = p_pair_from_q(q);
+        const unsigned ax = __float_as_uint(d.x) & 0x7fffffffu, ay = __float_as_uint(d.y) & 0x7fffffffu;
+        const bool sx = nA == 6 && (ax - 1u < 0x00ffffffu), sy = nB == 6 && (ay - 1u < 0x00ffffffu);
+        if (__any_sync(0xffffffffu, sx || sy)) { // only acc = 6 can miss (exhaustive check, see pressure_p_fast)
+            if (sx) P.x = __double2float_rn(__dmul_rn((double)div6_tiny(d.x), -1.9));
+            if (sy) P.y = __double2float_rn(__dmul_rn((double)div6_tiny(d.y), -1.9));
+        }
+        // old - 0 and old + 0 return old (up to the sign of a zero): a masked face keeps its value
+        U0 = __ffma2_rn(make_float2((cA & CODE_SX0) ? P.x : 0.f, (cB & CODE_SX0) ? P.y : 0.f), M1, U0);
+        U1 = __fadd2_rn(U1, make_float2((cA & CODE_SX1) ? P.x : 0.f, (cB & CODE_SX1) ? P.y : 0.f));
+        V0 = __ffma2_rn(make_float2((cA & CODE_SY0) ? P.x : 0.f, (cB & CODE_SY0) ? P.y : 0.f), M1, V0);
+        V1 = __fadd2_rn(V1, make_float2((cA & CODE_SY1) ? P.x : 0.f, (cB & CODE_SY1) ? P.y : 0.f));
+        W0 = __ffma2_rn(make_float2((cA & CODE_SZ0) ? P.x : 0.f, (cB & CODE_SZ0) ? P.y : 0.f), M1, W0);
+        W1 = __fadd2_rn(W1, make_float2((cA & CODE_SZ1) ? P.x : 0.f, (cB & CODE_SZ1) ? P.y : 0.f));
+    }
+    *reinterpret_cast<float2*>(pv) = V0;
+    *reinterpret_cast<float2*>(pv + RS) = V1;
+    if (PAR == 0) { ue = U0; uo = U1; we = W0; we1 = W1; }
+    else {
+        uo = U0; wo = W0; wo1 = W1;
+        ue.y = U1.x;
+        const float from_left = __shfl_up_sync(0xffffffffu, U1.y, 1); // the left quad's updated u[4h]
+        if (h != 0) ue.x = from_left;                                  // h == 0: tile edge, face stays stale (halo)
+    }
+}
+
+template <int K, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ vi, const float* __restrict__ wi,
+               float* __restrict__ uo, float* __restrict__ vo, float* __restrict__ wo,
+               const unsigned char* __restrict__ code, int sweep0, int zchunk)
+{
+    using C = RegCfg<K, NW>;
+    constexpr int LY = C::LY, RS = C::RS, HO = C::HO, R = C::R, PLS = C::PLS;
+    static_assert(K % 4 == 0 && NW % 2 == 0, "output region starts on a quad; both rows of a warp share the parity");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sv = reinterpret_cast<float*>(smem_raw); // [R][LY+1][RS]
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int h = lane & 15;                                 // quad index inside the row
+    const int yl = wid + (lane >> 4) * NW;                   // this half-warp's row
+    const int x0 = blockIdx.x * C::OX - K;
+    const int y0 = blockIdx.y * C::OY - K;
+    const int zo0 = g.zlo + blockIdx.z * zchunk;             // output node planes [zo0, zo1)
+    const int zo1 = min(zo0 + zchunk, g.zlo + g.nzn);
+    const int t0 = zo0 - K, t1 = zo1 + K - 1;                // planes that enter the ring
+    const int xg = x0 + 4 * h, yg = y0 + yl;
+
+    const bool nok = xg >= 0 && xg <= g.P - 4 && yg >= 0 && yg < g.SY;
+    const bool kok = xg >= 0 && xg <= g.PC - 4 && yg >= 0 && yg < g.H;
+    const bool sok = nok && yl >= K && yl < LY - K && h >= K / 4 && h < 16 - K / 4;
+    const int noff = nok ? xg + yg * g.P : 0;
+    const int koff = kok ? xg + yg * g.PC : 0;
+    const int vrow = yl * RS + 2 * h;                        // E[2h] of this lane's row inside a shared v plane
+    const int rowpar = (y0 + wid + sweep0 + 1) & 1;          // (+ t) = x parity of the active colour, warp uniform
+
+    for (int i = threadIdx.x; i < R * PLS; i += C::THREADS) sv[i] = 0.f; // dummy entries / dummy row: defined values
+    __syncthreads();
+
+    // register ring, index k = plane t-k
+    float2 UE[R], UO[R], WE[R], WO[R];
+    unsigned CW[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+        UE[k] = UO[k] = WE[k] = WO[k] = make_float2(0.f, 0.f);
+        CW[k] = 0;
+    }
+
+    float4 pu, pv, pw;
+    unsigned pc;
+    auto prefetch = [&](int z) {
+        const bool zn = z >= g.zlo && z < g.zlo + g.nzn;
+        const bool zc = z >= g.zlo && z < g.zlo + g.nzc;
+        pu = pv = pw = make_float4(0.f, 0.f, 0.f, 0.f);
+        pc = 0;
+        if (zn && nok) {
+            const long long n = (long long)(z - g.zlo) * g.nplane + noff;
+            pu = __ldg(reinterpret_cast<const float4*>(ui + n));
+            pv = __ldg(reinterpret_cast<const float4*>(vi + n));
+            pw = __ldg(reinterpret_cast<const float4*>(wi + n));
+        }
+        if (zc && kok) pc = __ldg(reinterpret_cast<const unsigned*>(code + (long long)(z - g.zlo) * g.kplane + koff));
+    };
+
+    prefetch(t0);
+    int slot_t = 0; // shared-memory slot of plane t (the same slot held plane t-K-1)
+    for (int t = t0; t <= t1 + 1; t++) {
+        // (a) v of plane t-K-1 became final with the previous step (behind its barrier): write it out, then reuse
+        //     the slot (same thread <-> same addresses, no barrier needed in between)
+        {
+            const int s2 = t - K - 1;
+            if (s2 >= zo0 && s2 < zo1 && sok) {
+                const float* p = sv + slot_t * PLS + vrow;
+                const float2 ve = *reinterpret_cast<const float2*>(p), vo2 = *reinterpret_cast<const float2*>(p + HO);
+                *reinterpret_cast<float4*>(vo + (long long)(s2 - g.zlo) * g.nplane + noff) = make_float4(ve.x, vo2.x, ve.y, vo2.y);
+            }
+        }
+        if (t > t1) break;
+        // (b) plane t enters: u, w and the code word into ring position 0, v into shared memory
+        UE[0] = make_float2(pu.x, pu.z); UO[0] = make_float2(pu.y, pu.w);
+        WE[0] = make_float2(pw.x, pw.z); WO[0] = make_float2(pw.y, pw.w);
+        CW[0] = pc;
+        {
+            float* p = sv + slot_t * PLS + vrow;
+            *reinterpret_cast<float2*>(p) = make_float2(pv.x, pv.z);
+            *reinterpret_cast<float2*>(p + HO) = make_float2(pv.y, pv.w);
+        }
+        if (t < t1) prefetch(t + 1); // in flight during the sweeps
+
+        // (c) sweep j runs on cell plane t-j with colour (sweep0+j-1)&1: the active x parity of a row,
+        //     (y + (t-j) + sweep0 + j - 1) & 1 = (y + t + sweep0 + 1) & 1, is the same for all K sweeps of this step.
+        //     No barrier between the sweeps: they touch different planes of v, and u / w are private to the lane.
+        const int par = (rowpar + t) & 1;
+        if (par) {
+#pragma unroll
+            for (int j = 1; j <= K; j++) {
+                if (t - j >= t0) {
+                    int sl = slot_t - j; if (sl < 0) sl += R;
+                    reg_update<1, RS, HO>(UE[j], UO[j], WE[j], WO[j], WE[j - 1], WO[j - 1], sv, sl * PLS + vrow, CW[j], h);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 1; j <= K; j++) {
+                if (t - j >= t0) {
+                    int sl = slot_t - j; if (sl < 0) sl += R;
+                    reg_update<0, RS, HO>(UE[j], UO[j], WE[j], WO[j], WE[j - 1], WO[j - 1], sv, sl * PLS + vrow, CW[j], h);
+                }
+            }
+        }
+
+        // (d) u and w of plane t-K are final and private to this lane: write them out now
+        {
+            const int s = t - K;
+            if (s >= zo0 && s < zo1 && sok) {
+                const long long n = (long long)(s - g.zlo) * g.nplane + noff;
+                *reinterpret_cast<float4*>(uo + n) = make_float4(UE[K].x, UO[K].x, UE[K].y, UO[K].y);
+                *reinterpret_cast<float4*>(wo + n) = make_float4(WE[K].x, WO[K].x, WE[K].y, WO[K].y);
+            }
+        }
+        // (e) shift the register ring
+#pragma unroll
+        for (int k = K; k >= 1; k--) {
+            UE[k] = UE[k - 1]; UO[k] = UO[k - 1]; WE[k] = WE[k - 1]; WO[k] = WO[k - 1]; CW[k] = CW[k - 1];
+        }
+        // (f) v faces written in this step are read by other rows in the next one
+        __syncthreads();
+        if (++slot_t == R) slot_t = 0;
+    }
+}
+
+} // namespace smk

@@ -19,6 +19,7 @@
 #include "grid.h"
 #include "kernels_basic.cuh"
 #include "kernels_pressure_fused.cuh"
+#include "kernels_pressure_reg.cuh"
 
 namespace {
 
@@ -221,6 +222,42 @@ int launch_halfsweep(smk_sim* s, int offset, int zlo_req = INT32_MIN, int zhi_re
 }
 
 // ---- fused pressure passes (kernels_pressure_fused.cuh) ---------------------------------------------------
+// z-chunking shared by the fused kernels: enough CTAs to fill the SMs, as few lead-in/lead-out planes
+// (2K per chunk) as possible
+int pick_zchunk(const smk_sim* s, int tiles_xy, int K)
+{
+    const GridP& g = s->g;
+    int best_n = 1;
+    double best = -1.0;
+    for (int n = 1; n <= std::max(1, g.nzn / 4); n++) {
+        const int zc = (g.nzn + n - 1) / n;
+        const long ctas = (long)tiles_xy * ((g.nzn + zc - 1) / zc);
+        const long waves = (ctas + s->num_sms - 1) / s->num_sms;
+        const double eff = (double)ctas / (double)(waves * s->num_sms) * (double)zc / (double)(zc + 2 * K);
+        if (eff > best + 1e-9) { best = eff; best_n = n; }
+    }
+    return (g.nzn + best_n - 1) / best_n;
+}
+
+int ensure_scratch(smk_sim* s)
+{
+    if (s->scratch[0]) return SMK_OK;
+    const size_t nb = node_count(s->g) * sizeof(float);
+    for (int i = 0; i < 3; i++) {
+        CK(s, cudaMalloc(&s->scratch[i], nb));
+        CK(s, cudaMemsetAsync(s->scratch[i], 0, nb, s->stream));
+    }
+    return SMK_OK;
+}
+
+void swap_in_scratch(smk_sim* s)
+{
+    const int n = s->now;
+    std::swap(s->u[n], s->scratch[0]);
+    std::swap(s->v[n], s->scratch[1]);
+    std::swap(s->w[n], s->scratch[2]);
+}
+
 template <int K, int FUSED_NW, int FUSED_RPW>
 int launch_fused_pass_cfg(smk_sim* s, int sweep0)
 {
@@ -232,32 +269,40 @@ int launch_fused_pass_cfg(smk_sim* s, int sweep0)
         CK(s, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         configured = true;
     }
-    if (!s->scratch[0]) {
-        const size_t nb = node_count(g) * sizeof(float);
-        for (int i = 0; i < 3; i++) {
-            CK(s, cudaMalloc(&s->scratch[i], nb));
-            CK(s, cudaMemsetAsync(s->scratch[i], 0, nb, s->stream));
-        }
-    }
+    int rc = ensure_scratch(s);
+    if (rc) return rc;
     const int tx = (g.W + 1 + C::OX - 1) / C::OX, ty = (g.SY + C::OY - 1) / C::OY;
-    // z-chunking: enough CTAs to fill the SMs, as few lead-in/lead-out planes (2K per chunk) as possible
-    int best_n = 1;
-    double best = -1.0;
-    for (int n = 1; n <= std::max(1, g.nzn / 4); n++) {
-        const int zc = (g.nzn + n - 1) / n;
-        const long ctas = (long)tx * ty * ((g.nzn + zc - 1) / zc);
-        const long waves = (ctas + s->num_sms - 1) / s->num_sms;
-        const double eff = (double)ctas / (double)(waves * s->num_sms) * (double)zc / (double)(zc + 2 * K);
-        if (eff > best + 1e-9) { best = eff; best_n = n; }
-    }
-    const int zchunk = (g.nzn + best_n - 1) / best_n;
+    const int zchunk = pick_zchunk(s, tx * ty, K);
     const dim3 grid((unsigned)tx, (unsigned)ty, (unsigned)((g.nzn + zchunk - 1) / zchunk));
     const int n = s->now;
     kern<<<grid, C::THREADS, C::SMEM, s->stream>>>(g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2],
                                                     s->code, sweep0, zchunk);
-    std::swap(s->u[n], s->scratch[0]);
-    std::swap(s->v[n], s->scratch[1]);
-    std::swap(s->w[n], s->scratch[2]);
+    swap_in_scratch(s);
+    count_launch(s, SMK_STAGE_PRESSURE);
+    return SMK_OK;
+}
+
+// register-resident fused pass (kernels_pressure_reg.cuh): u, w in registers, v in shared memory
+template <int K, int NW>
+int launch_reg_pass(smk_sim* s, int sweep0)
+{
+    using C = smk::RegCfg<K, NW>;
+    const GridP& g = s->g;
+    static bool configured = false;
+    auto kern = smk::k_pressure_reg<K, NW>;
+    if (!configured) {
+        CK(s, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        configured = true;
+    }
+    int rc = ensure_scratch(s);
+    if (rc) return rc;
+    const int tx = (g.W + 1 + C::OX - 1) / C::OX, ty = (g.SY + C::OY - 1) / C::OY;
+    const int zchunk = pick_zchunk(s, tx * ty, K);
+    const dim3 grid((unsigned)tx, (unsigned)ty, (unsigned)((g.nzn + zchunk - 1) / zchunk));
+    const int n = s->now;
+    kern<<<grid, C::THREADS, C::SMEM, s->stream>>>(g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2],
+                                                    s->code, sweep0, zchunk);
+    swap_in_scratch(s);
     count_launch(s, SMK_STAGE_PRESSURE);
     return SMK_OK;
 }
@@ -266,7 +311,8 @@ template <int K>
 int launch_fused_pass(smk_sim* s, int sweep0)
 {
     // tile shape (warps x rows per warp); tuning knob SMK_FUSED_CFG for experiments, default 24x2
-    static const int cfg = getenv("SMK_FUSED_CFG") ? atoi(getenv("SMK_FUSED_CFG")) : 242;
+    static const int cfg = getenv("SMK_FUSED_CFG") ? atoi(getenv("SMK_FUSED_CFG")) : 0;
+    if (K == 4 && cfg == 0) return launch_reg_pass<4, 16>(s, sweep0);
     switch (cfg) {
     case 163: return launch_fused_pass_cfg<K, 16, 3>(s, sweep0);
     case 124: return launch_fused_pass_cfg<K, 12, 4>(s, sweep0);
