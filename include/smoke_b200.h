@@ -65,10 +65,25 @@ enum {
  * reference leaves them uninitialised).  Mask: fluid everywhere, solid on y == 0. */
 int smk_create(smk_sim** out, unsigned W, unsigned H, unsigned D, const float* smoke0_host);
 
-/* one z-slab of a W x H x D grid for multi-GPU runs (no reference counterpart).
- * The slab owns cell planes [z_begin, z_end) and keeps `ghost` extra planes on each inner side. */
-int smk_create_slab(smk_sim** out, unsigned W, unsigned H, unsigned D, unsigned z_begin, unsigned z_end,
+/* one z-slab of a W x H x D grid for multi-GPU runs (no reference counterpart): slab `rank` of
+ * `world` owns cell planes [D*rank/world, D*(rank+1)/world) and keeps `ghost` (>= 4) extra planes on each interior
+ * side.  smoke0_host_full is the FULL W*H*D initial density (or NULL).  The step then needs a halo transport
+ * (smk_set_exchange); results are bit-identical to the single-GPU run. */
+int smk_create_slab(smk_sim** out, unsigned W, unsigned H, unsigned D, unsigned rank, unsigned world,
                     unsigned ghost, const float* smoke0_host_full);
+
+/* host-only (no CUDA call): slab geometry, the operation list smk_step executes for `steps` consecutive steps
+ * starting from replicated initial fields, and the halo regions of an exchange -- the same code smk_step uses.
+ *   out8 = {c0, c1, zlo, zhc, ghost, ok, own_node_lo, own_node_hi}
+ *   ops5: 5 ints per op {kind, a, b, p0, p1}; kind 0 flip, 1 fill, 2 force+clamp [a,b), 3 pressure pass (first
+ *         half-sweep p0, count p1), 4 advect u,v,w nodes [a,b) (valid input planes [p0,p1]), 5 advect density cells
+ *         [a,b), 6 exchange (a = set: 0 u,v,w "now", 1 density "now").  Returns the number of ops.
+ *   out5: 5 ints per region {side, send_lo, send_n, recv_lo, recv_n} in global plane indices. */
+int smk_slab_geometry(unsigned W, unsigned H, unsigned D, unsigned world, unsigned rank, unsigned ghost, int* out8);
+int smk_slab_plan(unsigned W, unsigned H, unsigned D, unsigned world, unsigned rank, unsigned ghost, int iterations,
+                  int fuse, int steps, int* ops5, int max_ops);
+int smk_slab_regions(unsigned W, unsigned H, unsigned D, unsigned world, unsigned rank, unsigned ghost, int set,
+                     int* out5, int max_regions);
 
 /* replaces deleteVolume()  (smokeSimulation.cuh:9, cu:240-248) */
 int smk_destroy(smk_sim* s);
@@ -143,17 +158,23 @@ long smk_launch_count(smk_sim* s);
 
 /* ---- multi-GPU halo transport (slab mode) --------------------------------------------------------------- */
 /* Caller-provided exchange: called from smk_step when ghost planes of a field set must be refreshed.
- * set: 0 = u,v,w "now", 1 = density "now".  For every listed region the callee must send `send_ptr`
- * (device, contiguous, `bytes` long) to the neighbour on `side` (0 = lower z, 1 = upper z) and receive
- * the neighbour's matching planes into `recv_ptr`.  All work must be ordered on `cuda_stream`. */
+ * set: 0 = u,v,w "now" (three regions per neighbour, in the order u, v, w), 1 = density "now".  For every listed
+ * region the callee must send `send_ptr` (device, contiguous, `send_bytes`) to the neighbour on `side` (0 = lower z,
+ * 1 = upper z) and receive the neighbour's matching planes (`recv_bytes`) into `recv_ptr`.  All work must be ordered
+ * on `cuda_stream`. */
 typedef struct {
-    int side;       /* 0 = lower-z neighbour, 1 = upper-z neighbour */
-    void* send_ptr; /* my owned boundary planes */
-    void* recv_ptr; /* my ghost planes          */
-    size_t bytes;
+    int side;          /* 0 = lower-z neighbour, 1 = upper-z neighbour */
+    void* send_ptr;    /* my owned boundary planes */
+    void* recv_ptr;    /* my ghost planes          */
+    size_t send_bytes; /* (u,v,w have one more upper-ghost plane than they send up: sizes differ per direction) */
+    size_t recv_bytes;
 } smk_halo_region;
 typedef int (*smk_exchange_fn)(void* ctx, int set, const smk_halo_region* regions, int nregions, void* cuda_stream);
 int smk_set_exchange(smk_sim* s, smk_exchange_fn fn, void* ctx);
+
+/* execute ONE operation of a plan returned by smk_slab_plan (op5 = {kind, a, b, p0, p1}); an exchange op calls the
+ * transport.  smk_step == every op of plan_step in order.  Used by tests to drive several slabs in lock-step. */
+int smk_exec_op(smk_sim* s, const int* op5, float dt);
 
 const char* smk_last_error(smk_sim* s);
 int smk_abi_version(void);

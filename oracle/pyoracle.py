@@ -110,6 +110,9 @@ class Oracle(_Engine):
             for n in ("integrate", "clamp", "advect_velocity", "advect_smoke"):
                 getattr(L, "orc_" + n).argtypes = [_vp, _f]
             L.orc_pressure_halfsweep.argtypes = [_vp, C.c_int]
+            for n in ("integrate_r", "clamp_r", "advect_velocity_r", "advect_smoke_r"):
+                getattr(L, "orc_" + n).argtypes = [_vp, _f, C.c_int, C.c_int]
+            L.orc_pressure_halfsweep_r.argtypes = [_vp, C.c_int, C.c_int, C.c_int]
             L.orc_get_field.argtypes = [_vp, C.c_int, C.c_int, _vp]
             L.orc_set_field.argtypes = [_vp, C.c_int, C.c_int, _vp]
             L.orc_index_now.argtypes = [_vp]
@@ -159,6 +162,12 @@ class Oracle(_Engine):
     def index_now(self): return self.lib().orc_index_now(self.h)
     def _get(self, f, w, p): self.lib().orc_get_field(self.h, f, w, p)
     def _set(self, f, w, p): self.lib().orc_set_field(self.h, f, w, p)
+    # plane-range variants (z-slab emulation)
+    def integrate_r(self, dt, za, zb): self.lib().orc_integrate_r(self.h, dt, za, zb)
+    def clamp_r(self, dt, za, zb): self.lib().orc_clamp_r(self.h, dt, za, zb)
+    def pressure_halfsweep_r(self, offset, za, zb): self.lib().orc_pressure_halfsweep_r(self.h, offset, za, zb)
+    def advect_velocity_r(self, dt, za, zb): self.lib().orc_advect_velocity_r(self.h, dt, za, zb)
+    def advect_smoke_r(self, dt, za, zb): self.lib().orc_advect_smoke_r(self.h, dt, za, zb)
 
 
 class RefCPU(_Engine):

@@ -187,14 +187,19 @@ void orc_fill(smk_oracle* o)
 /* cu:315-329.  v-face (x,y,z), x in [0,W), y in [1,H), z in [0,D), both cells fluid:
  *   v += smoke*gravity*dt + (alpha*smoke)*dt        (smoke of the upper cell)
  * nvcc (SASS): t = fma(smoke*gravity, dt, (smoke*alpha)*dt); v = t + v. */
-void orc_integrate(smk_oracle* o, float dt)
+void orc_integrate(smk_oracle* o, float dt) { orc_integrate_r(o, dt, 0, o->D); }
+
+/* the same on node planes [za, zb) only (z-slab emulation in tests/test_slab_cpu.py) */
+void orc_integrate_r(smk_oracle* o, float dt, int za, int zb)
 {
     const int W = o->W, H = o->H, D = o->D, ct = o->contract;
+    if (za < 0) za = 0;
+    if (zb > D) zb = D;
     float* v = o->v[o->now];
     const float* smoke = o->smoke[o->now];
     const float g = o->gravity, alpha = o->alpha;
 #pragma omp parallel for schedule(static)
-    for (int z = 0; z < D; z++)
+    for (int z = za; z < zb; z++)
         for (int y = 1; y < H; y++)
             for (int x = 0; x < W; x++) {
                 if (!o->s[cidx(o, x, y, z)] || !o->s[cidx(o, x, y - 1, z)]) continue;
@@ -209,12 +214,16 @@ void orc_integrate(smk_oracle* o, float dt)
 /* cu:331-352 (the max-velocity clamp).  Same staggered index for the three components,
  * x,y,z in [1,W) x [1,H) x [1,D):  L = u^2+v^2+w^2;  if L*dt > 9: scale by 9/(L*dt).
  * nvcc (SASS): L = fma(w,w, fma(u,u, v*v)); one IEEE divide shared by the three products. */
-void orc_clamp(smk_oracle* o, float dt)
+void orc_clamp(smk_oracle* o, float dt) { orc_clamp_r(o, dt, 0, o->D); }
+
+void orc_clamp_r(smk_oracle* o, float dt, int za, int zb)
 {
     const int W = o->W, H = o->H, D = o->D, ct = o->contract;
     float *u = o->u[o->now], *v = o->v[o->now], *w = o->w[o->now];
+    if (za < 1) za = 1;
+    if (zb > D) zb = D;
 #pragma omp parallel for schedule(static)
-    for (int z = 1; z < D; z++)
+    for (int z = za; z < zb; z++)
         for (int y = 1; y < H; y++)
             for (int x = 1; x < W; x++) {
                 size_t f = sidx(o, x, y, z);
@@ -238,13 +247,18 @@ void orc_clamp(smk_oracle* o, float dt)
  *   u0 -= p*sx0; u1 += p*sx1; v0 -= p*sy0; v1 += p*sy1; w0 -= p*sz0; w1 += p*sz1
  * p*s is exact (s in {0,1}), so contraction does not change the result here.
  * Same-colour cells share no face, so the loop is race-free in any order. */
-void orc_pressure_halfsweep(smk_oracle* o, int offset)
+void orc_pressure_halfsweep(smk_oracle* o, int offset) { orc_pressure_halfsweep_r(o, offset, 0, o->D); }
+
+/* the same on cell planes [za, zb) only */
+void orc_pressure_halfsweep_r(smk_oracle* o, int offset, int za, int zb)
 {
     const int W = o->W, H = o->H, D = o->D;
     float *u = o->u[o->now], *v = o->v[o->now], *w = o->w[o->now];
     const unsigned char* s = o->s;
+    if (za < 1) za = 1;
+    if (zb > D - 1) zb = D - 1;
 #pragma omp parallel for schedule(static)
-    for (int z = 1; z < D - 1; z++)
+    for (int z = za; z < zb; z++)
         for (int y = 1; y < H - 1; y++) {
             int x = 1 + ((1 + y + z + offset) & 1); /* first interior x with (x+y+z+offset) even */
             for (; x < W - 1; x += 2) {
@@ -376,14 +390,19 @@ static inline float backtrace(int ct, float pos0, float vel, float dt)
  *   V (cu:557-585): x in [1,W-1), y in [1,H), z in [1,D-1); s[y]&&s[y-1]; pos (x+.5, y, z+.5)
  *   W (cu:587-615): x in [1,W-1), y in [1,H-1), z in [1,D); s[z]&&s[z-1]; pos (x+.5, y+.5, z)
  * "i + 0.5" is evaluated in double and narrowed (cu:536-537 etc.). */
-void orc_advect_velocity(smk_oracle* o, float dt)
+void orc_advect_velocity(smk_oracle* o, float dt) { orc_advect_velocity_r(o, dt, 0, o->D); }
+
+/* the same on node planes [za, zb) only */
+void orc_advect_velocity_r(smk_oracle* o, float dt, int za, int zb)
 {
     const int W = o->W, H = o->H, D = o->D, SX = o->SX, SY = o->SY, ct = o->contract;
+    if (za < 1) za = 1;
+    if (zb > D) zb = D;
     const float *u0 = o->u[o->now], *v0 = o->v[o->now], *w0 = o->w[o->now];
     float *u1 = o->u[o->past], *v1 = o->v[o->past], *w1 = o->w[o->past];
     const unsigned char* s = o->s;
 #pragma omp parallel for schedule(static)
-    for (int z = 1; z < D; z++)
+    for (int z = za; z < zb; z++)
         for (int y = 1; y < H; y++)
             for (int x = 1; x < W; x++) {
                 size_t f = sidx(o, x, y, z);
@@ -413,14 +432,19 @@ void orc_advect_velocity(smk_oracle* o, float dt)
  * orc_advect_velocity; cu:810).  Interior fluid cells only.
  *   u_t = (u[x] + u[x+1]) / 2 ...;  pos = (float)((double)x + 0.5 - (double)(u_t*dt))
  * (u_t*dt is a float product, widened; the subtraction is in double: cu:628-630). */
-void orc_advect_smoke(smk_oracle* o, float dt)
+void orc_advect_smoke(smk_oracle* o, float dt) { orc_advect_smoke_r(o, dt, 0, o->D); }
+
+/* the same on cell planes [za, zb) only */
+void orc_advect_smoke_r(smk_oracle* o, float dt, int za, int zb)
 {
     const int W = o->W, H = o->H, D = o->D;
     const float *u = o->u[o->past], *v = o->v[o->past], *w = o->w[o->past];
     const float* s0 = o->smoke[o->now];
     float* s1 = o->smoke[o->past];
+    if (za < 1) za = 1;
+    if (zb > D - 1) zb = D - 1;
 #pragma omp parallel for schedule(static)
-    for (int z = 1; z < D - 1; z++)
+    for (int z = za; z < zb; z++)
         for (int y = 1; y < H - 1; y++)
             for (int x = 1; x < W - 1; x++) {
                 size_t c = cidx(o, x, y, z);

@@ -62,6 +62,14 @@ void orc_pressure_halfsweep(smk_oracle* o, int offset); /* cu:356-394 */
 void orc_advect_velocity(smk_oracle* o, float dt);      /* cu:527-615 */
 void orc_advect_smoke(smk_oracle* o, float dt);         /* cu:617-638 */
 
+/* the same stages restricted to a plane range [za, zb) (nodes for integrate / clamp / advect_velocity, cells for
+ * the others): used by tests/test_slab_cpu.py to execute the multi-GPU z-slab schedule on the CPU */
+void orc_integrate_r(smk_oracle* o, float dt, int za, int zb);
+void orc_clamp_r(smk_oracle* o, float dt, int za, int zb);
+void orc_pressure_halfsweep_r(smk_oracle* o, int offset, int za, int zb);
+void orc_advect_velocity_r(smk_oracle* o, float dt, int za, int zb);
+void orc_advect_smoke_r(smk_oracle* o, float dt, int za, int zb);
+
 /* which: 0 = buffer indexNow, 1 = buffer tempIndexPast, 2/3 = physical buffer 0/1 */
 void orc_get_field(const smk_oracle* o, int field, int which, void* dst);
 void orc_set_field(smk_oracle* o, int field, int which, const void* src);

@@ -8,6 +8,7 @@ bench.py: a ctypes binding (``binding.py``) and the multi-GPU slab plumbing (``s
 The directory name contains a hyphen; import it as ``smoke_simulation_b200`` (the module of that name at
 the repository root points its ``__path__`` here).
 """
+from . import slab  # noqa: F401
 from .binding import (  # noqa: F401
     LIB_PATH, SmokeSim, SmokeError, load_library, build_library, declared_symbols,
     SMOKE, U, V, W, MASK, NOW, PAST, BUF0, BUF1,

@@ -32,7 +32,7 @@ class SmokeError(RuntimeError):
 
 
 class HaloRegion(C.Structure):
-    _fields_ = [("side", _i), ("send_ptr", _vp), ("recv_ptr", _vp), ("bytes", C.c_size_t)]
+    _fields_ = [("side", _i), ("send_ptr", _vp), ("recv_ptr", _vp), ("send_bytes", C.c_size_t), ("recv_bytes", C.c_size_t)]
 
 
 EXCHANGE_FN = C.CFUNCTYPE(_i, _vp, _i, C.POINTER(HaloRegion), _i, _vp)
@@ -62,6 +62,9 @@ def load_library():
     L = C.CDLL(LIB_PATH)
     L.smk_create.argtypes = [C.POINTER(_vp), C.c_uint, C.c_uint, C.c_uint, _vp]
     L.smk_create_slab.argtypes = [C.POINTER(_vp)] + [C.c_uint] * 6 + [_vp]
+    L.smk_slab_geometry.argtypes = [C.c_uint] * 6 + [C.POINTER(_i)]
+    L.smk_slab_plan.argtypes = [C.c_uint] * 6 + [_i, _i, _i, C.POINTER(_i), _i]
+    L.smk_slab_regions.argtypes = [C.c_uint] * 6 + [_i, C.POINTER(_i), _i]
     L.smk_destroy.argtypes = [_vp]
     L.smk_add_obstacle.argtypes = [_vp] + [_f] * 7
     L.smk_add_source.argtypes = [_vp] + [_f] * 4
@@ -93,6 +96,7 @@ def load_library():
     L.smk_launch_count.argtypes = [_vp]
     L.smk_launch_count.restype = C.c_long
     L.smk_set_exchange.argtypes = [_vp, EXCHANGE_FN, _vp]
+    L.smk_exec_op.argtypes = [_vp, C.POINTER(_i), _f]
     L.smk_last_error.argtypes = [_vp]
     L.smk_last_error.restype = C.c_char_p
     _lib = L
@@ -112,7 +116,8 @@ def field_dtype(field):
 class SmokeSim:
     """One simulation volume on the current CUDA device (reference: the process globals of cu:16-58)."""
 
-    def __init__(self, W_, H_, D_, smoke0=None, slab=None, ghost=0):
+    def __init__(self, W_, H_, D_, smoke0=None, slab=None, ghost=8):
+        """slab = (rank, world) creates one z-slab of a multi-GPU run (smk_create_slab)."""
         self.L = load_library()
         self.W, self.H, self.D = int(W_), int(H_), int(D_)
         self.h = _vp()
@@ -225,12 +230,19 @@ class SmokeSim:
     def reset_timers(self): self._ck(self.L.smk_reset_timers(self.h))
     def launch_count(self): return int(self.L.smk_launch_count(self.h))
 
+    def exec_op(self, op, dt):
+        """Run one plan op; `op` = (name-or-kind, a, b, p0, p1) as returned by slab.plan()."""
+        from .slab import OP_NAMES
+        kind = OP_NAMES.index(op[0]) if isinstance(op[0], str) else int(op[0])
+        arr = (_i * 5)(kind, *[int(v) for v in op[1:5]])
+        self._ck(self.L.smk_exec_op(self.h, arr, dt))
+
     def set_exchange(self, pyfunc):
-        """pyfunc(set_id, [(side, send_ptr, recv_ptr, bytes), ...], stream_ptr) -> int"""
+        """pyfunc(set_id, [(side, send_ptr, recv_ptr, send_bytes, recv_bytes), ...], stream_ptr) -> int"""
         def tramp(ctx, set_id, regions, n, stream):
             try:
-                return int(pyfunc(set_id, [(regions[i].side, regions[i].send_ptr, regions[i].recv_ptr, regions[i].bytes)
-                                           for i in range(n)], stream) or 0)
+                return int(pyfunc(set_id, [(regions[i].side, regions[i].send_ptr, regions[i].recv_ptr, regions[i].send_bytes,
+                                            regions[i].recv_bytes) for i in range(n)], stream) or 0)
             except Exception:  # pragma: no cover - surfaced as SMK_ERR_TRANSPORT
                 import traceback
                 traceback.print_exc()

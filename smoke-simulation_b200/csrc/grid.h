@@ -21,6 +21,8 @@ struct GridP {
     int nzn;          // stored node planes  [zlo, zlo + nzn), nzn = nzc + 1
     int PC;           // row pitch of the stencil-code array in bytes = roundup(W, 16) (pad bytes are 0)
     long long kplane; // plane stride of the stencil-code array = PC * H
+    int mzlo;         // first stored MASK plane: a slab keeps one more mask plane than cell planes on each interior
+    int nzm;          // side so that the stencil codes of its outermost stored cells are right; [mzlo, mzlo + nzm)
 };
 
 // stencil code byte per cell, derived from the mask after every fill

@@ -23,6 +23,10 @@ __device__ __forceinline__ long long cell_index(const GridP& g, int x, int y, in
 {
     return (long long)x + (long long)y * g.W + (long long)(z - g.zlo) * g.cplane;
 }
+__device__ __forceinline__ long long mask_index(const GridP& g, int x, int y, int z)
+{
+    return (long long)x + (long long)y * g.W + (long long)(z - g.mzlo) * g.cplane;
+}
 __device__ __forceinline__ long long code_index(const GridP& g, int x, int y, int z)
 {
     return (long long)x + (long long)y * g.PC + (long long)(z - g.zlo) * g.kplane;
@@ -41,14 +45,16 @@ __global__ void __launch_bounds__(256) k_fill(GridP g, float* __restrict__ smoke
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.W * g.H) return;
     const int y = i / g.W, x = i - y * g.W;
-    const int z = za + blockIdx.y;
+    const int z = za + blockIdx.y; // walks the stored MASK planes (one more than the cell planes on slab-interior sides)
     if (x < 1 || y < 1 || z < 1 || x >= g.W - 1 || y >= g.H - 1 || z >= g.D - 1) return;
-    const long long c = cell_index(g, x, y, z);
-    for (int k = 0; k < o.nsrc; k++) {
-        float dist = powf(x - o.src[k][0], 2) + powf(y - o.src[k][1], 2) + powf(z - o.src[k][2], 2);
-        if (dist < o.src[k][3] * o.src[k][3]) {
-            smoke0[c] = 1.0f;
-            smoke1[c] = 1.0f;
+    if (z >= g.zlo && z < g.zlo + g.nzc) {
+        const long long c = cell_index(g, x, y, z);
+        for (int k = 0; k < o.nsrc; k++) {
+            float dist = powf(x - o.src[k][0], 2) + powf(y - o.src[k][1], 2) + powf(z - o.src[k][2], 2);
+            if (dist < o.src[k][3] * o.src[k][3]) {
+                smoke0[c] = 1.0f;
+                smoke1[c] = 1.0f;
+            }
         }
     }
     if (o.nobs > 0) {
@@ -57,7 +63,7 @@ __global__ void __launch_bounds__(256) k_fill(GridP g, float* __restrict__ smoke
             float dist = powf(x - o.obs[k][0], 2) + powf(y - o.obs[k][1], 2) + powf(z - o.obs[k][2], 2);
             sv = (dist < o.obs[k][3] * o.obs[k][3]) ? 0 : 1;
         }
-        mask[c] = sv;
+        mask[mask_index(g, x, y, z)] = sv;
     }
 }
 
@@ -73,15 +79,15 @@ __global__ void __launch_bounds__(256) k_codes(GridP g, const unsigned char* __r
     if (i >= g.W * g.H) return;
     const int y = i / g.W, x = i - y * g.W;
     const int z = za + blockIdx.y;
-    const long long c = cell_index(g, x, y, z);
-    const int zhi = g.zlo + g.nzc; // first cell plane not stored
+    const long long c = mask_index(g, x, y, z);
+    const int mhi = g.mzlo + g.nzm; // first mask plane not stored
     unsigned v = 0;
     if (x > 0 && mask[c - 1]) v |= CODE_SX0;
     if (x < g.W - 1 && mask[c + 1]) v |= CODE_SX1;
     if (y > 0 && mask[c - g.W]) v |= CODE_SY0;
     if (y < g.H - 1 && mask[c + g.W]) v |= CODE_SY1;
-    if (z > g.zlo && mask[c - g.cplane]) v |= CODE_SZ0;
-    if (z < zhi - 1 && mask[c + g.cplane]) v |= CODE_SZ1;
+    if (z > g.mzlo && mask[c - g.cplane]) v |= CODE_SZ0;
+    if (z < mhi - 1 && mask[c + g.cplane]) v |= CODE_SZ1;
     const bool interior = x >= 1 && y >= 1 && z >= 1 && x < g.W - 1 && y < g.H - 1 && z < g.D - 1;
     const bool self = mask[c] != 0;
     if (self) v |= CODE_SELF;
@@ -258,14 +264,20 @@ __device__ __forceinline__ float tri_combine(const Tri& t, float f000, float f10
     acc = __fmaf_rn(__fmul_rn(a11, t.zw1), f111, acc);
     return acc;
 }
+// `zv` = [lo, hi] planes of f that hold valid data (the whole domain on one GPU; the slab's current valid interval in
+// a multi-GPU run): a backtrace that leaves it raises *flag (-> SMK_ERR_REACH) instead of silently reading a stale ghost.
 __device__ __forceinline__ float sample_global(const float* __restrict__ f, long long sy, long long sz, int zlo,
                                                float px, float py, float pz, float dx, float dy, float dz,
-                                               float bx, float by, float bz)
+                                               float bx, float by, float bz, int2 zv, int* __restrict__ flag)
 {
     Tri t;
     tri_axis(px, dx, bx, t.x0, t.x1, t.xw0, t.xw1);
     tri_axis(py, dy, by, t.y0, t.y1, t.yw0, t.yw1);
     tri_axis(pz, dz, bz, t.z0, t.z1, t.zw0, t.zw1);
+    if (t.z0 < zv.x || t.z1 > zv.y) { // slab runs only; clamp so the load itself stays inside the stored planes
+        *flag = 1;
+        t.z0 = max(zv.x, min(zv.y, t.z0)); t.z1 = max(zv.x, min(zv.y, t.z1));
+    }
     const float* r00 = f + t.y0 * sy + (long long)(t.z0 - zlo) * sz;
     const float* r10 = f + t.y1 * sy + (long long)(t.z0 - zlo) * sz;
     const float* r01 = f + t.y0 * sy + (long long)(t.z1 - zlo) * sz;
@@ -327,7 +339,7 @@ __global__ void __launch_bounds__(256) k_advect_velocity(GridP g, const float* _
                                                          const float* __restrict__ v0, const float* __restrict__ w0,
                                                          float* __restrict__ u1, float* __restrict__ v1,
                                                          float* __restrict__ w1, const unsigned char* __restrict__ code,
-                                                         float dt, int za)
+                                                         float dt, int za, int2 zv, int* __restrict__ flag)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.P * g.SY) return;
@@ -352,19 +364,19 @@ __global__ void __launch_bounds__(256) k_advect_velocity(GridP g, const float* _
         const float px = __fmaf_rn(-u0[n], dt, (float)x);
         const float py = __fmaf_rn(-av, dt, yh);
         const float pz = __fmaf_rn(-aw, dt, zh);
-        u1[n] = sample_global(u0, P, S, g.zlo, px, py, pz, 0.f, .5f, .5f, bx, by, bz);
+        u1[n] = sample_global(u0, P, S, g.zlo, px, py, pz, 0.f, .5f, .5f, bx, by, bz, zv, flag);
     }
     if (doV) {
         const float px = __fmaf_rn(-au, dt, xh);
         const float py = __fmaf_rn(-v0[n], dt, (float)y);
         const float pz = __fmaf_rn(-aw, dt, zh);
-        v1[n] = sample_global(v0, P, S, g.zlo, px, py, pz, .5f, 0.f, .5f, bx, by, bz);
+        v1[n] = sample_global(v0, P, S, g.zlo, px, py, pz, .5f, 0.f, .5f, bx, by, bz, zv, flag);
     }
     if (doW) {
         const float px = __fmaf_rn(-au, dt, xh);
         const float py = __fmaf_rn(-av, dt, yh);
         const float pz = __fmaf_rn(-w0[n], dt, (float)z);
-        w1[n] = sample_global(w0, P, S, g.zlo, px, py, pz, .5f, .5f, 0.f, bx, by, bz);
+        w1[n] = sample_global(w0, P, S, g.zlo, px, py, pz, .5f, .5f, 0.f, bx, by, bz, zv, flag);
     }
 }
 
@@ -375,7 +387,7 @@ __global__ void __launch_bounds__(256) k_advect_velocity(GridP g, const float* _
 __global__ void __launch_bounds__(256) k_advect_smoke(GridP g, const float* __restrict__ s0, float* __restrict__ s1,
                                                       const float* __restrict__ u, const float* __restrict__ v,
                                                       const float* __restrict__ w, const unsigned char* __restrict__ code,
-                                                      float dt, int za)
+                                                      float dt, int za, int2 zv, int* __restrict__ flag)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.W * g.H) return;
@@ -392,7 +404,7 @@ __global__ void __launch_bounds__(256) k_advect_smoke(GridP g, const float* __re
     const float py = __double2float_rn(__dadd_rn(__dadd_rn((double)y, 0.5), (double)mv));
     const float pz = __double2float_rn(__dadd_rn(__dadd_rn((double)z, 0.5), (double)mw));
     const float bx = (float)(unsigned)(g.W - 1), by = (float)(unsigned)(g.H - 1), bz = (float)(unsigned)(g.D - 1);
-    s1[c] = sample_global(s0, g.W, g.cplane, g.zlo, px, py, pz, .5f, .5f, .5f, bx, by, bz);
+    s1[c] = sample_global(s0, g.W, g.cplane, g.zlo, px, py, pz, .5f, .5f, .5f, bx, by, bz, zv, flag);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -20,6 +20,7 @@
 #include "kernels_basic.cuh"
 #include "kernels_pressure_fused.cuh"
 #include "kernels_pressure_reg.cuh"
+#include "slab_plan.h"
 
 namespace {
 
@@ -60,10 +61,13 @@ struct smk_sim {
     int iterations = 30; // cu:797
     int fuse = 0;
 
-    // slab decomposition (single GPU: owns everything, no ghosts)
-    int c0 = 0, c1 = 0, ghost = 0;
+    // slab decomposition (single GPU: owns everything, no ghosts); schedule and validity tracking in slab_plan.h
+    slab::Geom geom{};
+    slab::Carry carry{};
     smk_exchange_fn exchange = nullptr;
     void* exchange_ctx = nullptr;
+    int* d_flags = nullptr; // [0]: a backtrace left the valid planes of a slab (SMK_ERR_REACH)
+    long exchanges = 0;
 
     // host buffers registered for fast density readback
     std::vector<void*> registered;
@@ -176,7 +180,7 @@ int stage_fill(smk_sim* s)
     const ObjP o = pack_objects(s);
     if (g.nzc > 0) {
         if (o.nsrc > 0 || o.nobs > 0) {
-            smk::k_fill<<<row_grid(g.cplane, g.nzc), 256, 0, s->stream>>>(g, s->smoke[0], s->smoke[1], s->mask, o, g.zlo);
+            smk::k_fill<<<row_grid(g.cplane, g.nzm), 256, 0, s->stream>>>(g, s->smoke[0], s->smoke[1], s->mask, o, g.mzlo);
             count_launch(s, SMK_STAGE_FILL);
         }
         smk::k_codes<<<row_grid(g.cplane, g.nzc), 256, 0, s->stream>>>(g, s->mask, s->code, g.zlo);
@@ -186,14 +190,19 @@ int stage_fill(smk_sim* s)
     return SMK_OK;
 }
 
-int stage_force_clamp(smk_sim* s, float dt)
+// node planes [za, zb)
+int stage_force_clamp(smk_sim* s, float dt, int za, int zb)
 {
     const GridP& g = s->g;
     Span sp(s, SMK_STAGE_FORCE);
     const int n = s->now;
-    smk::k_force_clamp<<<row_grid(g.nplane, g.nzc), 256, 0, s->stream>>>(g, s->u[n], s->v[n], s->w[n], s->smoke[n], s->code,
-                                                                        dt, s->gravity, s->alpha, g.zlo);
-    count_launch(s, SMK_STAGE_FORCE);
+    za = std::max(za, g.zlo);
+    zb = std::min(zb, std::min(g.D, g.zlo + g.nzc));
+    if (zb > za) {
+        smk::k_force_clamp<<<row_grid(g.nplane, zb - za), 256, 0, s->stream>>>(g, s->u[n], s->v[n], s->w[n], s->smoke[n],
+                                                                            s->code, dt, s->gravity, s->alpha, za);
+        count_launch(s, SMK_STAGE_FORCE);
+    }
     CK(s, cudaGetLastError());
     return SMK_OK;
 }
@@ -322,63 +331,65 @@ int launch_fused_pass(smk_sim* s, int sweep0)
     }
 }
 
+int effective_fuse(const smk_sim* s)
+{
+    if (s->fuse != 0) return s->fuse;
+    return (s->g.W + 1 < 32 || s->g.nzn < 8) ? 1 : 4; // tiny grids: tiles would be mostly halo
+}
+
+// half-sweeps [sweep0, sweep0 + K) on every stored plane (offsets alternate 0,1: cu:797-801)
+int run_pressure_pass(smk_sim* s, int sweep0, int K)
+{
+    if (K == 4) return launch_fused_pass<4>(s, sweep0);
+    if (K == 2) return launch_fused_pass<2>(s, sweep0);
+    return launch_halfsweep(s, sweep0 & 1);
+}
+
 int stage_pressure(smk_sim* s)
 {
     Span sp(s, SMK_STAGE_PRESSURE);
-    const int total = 2 * s->iterations; // half-sweeps, alternating offset 0,1 (cu:797-801)
-    int fuse = s->fuse;
-    if (fuse == 0) fuse = (s->g.W + 1 < 32 || s->g.nzn < 8) ? 1 : 4; // tiny grids: tiles would be mostly halo
+    const int total = 2 * s->iterations;
+    const int fuse = effective_fuse(s);
     int done = 0, rc = SMK_OK;
-    // EXPERIMENT (env SMK_L2_ZC / SMK_L2_G): L2-resident wavefront of the unfused kernel.  Groups of G
-    // half-sweeps are applied chunk by chunk (Zc planes), sweep j shifted down by j planes, so the planes
-    // a group touches stay in the 126 MB L2 between launches.  Same per-cell order of updates => same bits.
-    static const int l2_zc = getenv("SMK_L2_ZC") ? atoi(getenv("SMK_L2_ZC")) : 0;
-    static const int l2_g = getenv("SMK_L2_G") ? atoi(getenv("SMK_L2_G")) : 20;
-    if (fuse == 1 && l2_zc > 0) {
-        const GridP& g = s->g;
-        while (done < total) {
-            const int G = std::min(l2_g, total - done);
-            for (int c0 = 0; c0 - G < g.D; c0 += l2_zc)
-                for (int j = 0; j < G; j++) launch_halfsweep(s, (done + j) & 1, c0 - j, c0 + l2_zc - j);
-            done += G;
-        }
-    }
     while (done < total && rc == SMK_OK) {
         const int left = total - done;
-        if (fuse >= 4 && left >= 4 && (done & 1) == 0) { rc = launch_fused_pass<4>(s, done); done += 4; }
-        else if (fuse >= 2 && left >= 2 && (done & 1) == 0) { rc = launch_fused_pass<2>(s, done); done += 2; }
-        else { rc = launch_halfsweep(s, done & 1); done += 1; }
+        const int K = (fuse >= 4 && left >= 4 && (done & 1) == 0) ? 4 : (fuse >= 2 && left >= 2 && (done & 1) == 0) ? 2 : 1;
+        rc = run_pressure_pass(s, done, K);
+        done += K;
     }
     if (rc) return rc;
     CK(s, cudaGetLastError());
     return SMK_OK;
 }
 
-int stage_advect_velocity(smk_sim* s, float dt)
+// node planes [za, zb); [vlo, vhi] = planes of the "now" velocities that hold valid data (reach guard)
+int stage_advect_velocity(smk_sim* s, float dt, int za, int zb, int vlo, int vhi)
 {
     const GridP& g = s->g;
     Span sp(s, SMK_STAGE_ADVECT_VEL);
     const int n = s->now, p = s->past;
-    const int za = std::max(1, g.zlo), zb = std::min(g.D, g.zlo + g.nzc);
+    za = std::max(za, std::max(1, g.zlo));
+    zb = std::min(zb, std::min(g.D, g.zlo + g.nzc));
     if (zb > za) {
-        smk::k_advect_velocity<<<row_grid(g.nplane, zb - za), 256, 0, s->stream>>>(g, s->u[n], s->v[n], s->w[n], s->u[p],
-                                                                               s->v[p], s->w[p], s->code, dt, za);
+        smk::k_advect_velocity<<<row_grid(g.nplane, zb - za), 256, 0, s->stream>>>(
+            g, s->u[n], s->v[n], s->w[n], s->u[p], s->v[p], s->w[p], s->code, dt, za, make_int2(vlo, vhi), s->d_flags);
         count_launch(s, SMK_STAGE_ADVECT_VEL);
     }
     CK(s, cudaGetLastError());
     return SMK_OK;
 }
 
-int stage_advect_smoke(smk_sim* s, float dt)
+// cell planes [za, zb); [vlo, vhi] = cell planes of the "now" density that hold valid data
+int stage_advect_smoke(smk_sim* s, float dt, int za, int zb, int vlo, int vhi)
 {
     const GridP& g = s->g;
     Span sp(s, SMK_STAGE_ADVECT_SMOKE);
     const int n = s->now, p = s->past;
-    int za, zb;
-    pressure_planes(g, za, zb);
+    za = std::max(za, std::max(1, g.zlo));
+    zb = std::min(zb, std::min(g.D - 1, g.zlo + g.nzc));
     if (zb > za) {
-        smk::k_advect_smoke<<<row_grid(g.cplane, zb - za), 256, 0, s->stream>>>(g, s->smoke[n], s->smoke[p], s->u[p], s->v[p],
-                                                                            s->w[p], s->code, dt, za);
+        smk::k_advect_smoke<<<row_grid(g.cplane, zb - za), 256, 0, s->stream>>>(
+            g, s->smoke[n], s->smoke[p], s->u[p], s->v[p], s->w[p], s->code, dt, za, make_int2(vlo, vhi), s->d_flags);
         count_launch(s, SMK_STAGE_ADVECT_SMOKE);
     }
     CK(s, cudaGetLastError());
@@ -407,21 +418,64 @@ bool try_register(smk_sim* s, void* p, size_t bytes)
     return true;
 }
 
+// halo exchange of one field set through the caller's transport (smk_set_exchange)
+int run_exchange(smk_sim* s, int set)
+{
+    if (!s->exchange) return fail(s, SMK_ERR_TRANSPORT, "slab step needs a halo transport: call smk_set_exchange() first");
+    const GridP& g = s->g;
+    std::vector<smk_halo_region> out;
+    for (const slab::Region& r : slab::regions(s->geom, set)) {
+        if (set == slab::SET_VEL_NOW) {
+            float* f[3] = {s->u[s->now], s->v[s->now], s->w[s->now]};
+            for (int i = 0; i < 3; i++)
+                out.push_back({r.side, f[i] + (size_t)(r.send_lo - g.zlo) * g.nplane, f[i] + (size_t)(r.recv_lo - g.zlo) * g.nplane,
+                               (size_t)r.send_n * g.nplane * sizeof(float), (size_t)r.recv_n * g.nplane * sizeof(float)});
+        } else {
+            float* f = s->smoke[s->now];
+            out.push_back({r.side, f + (size_t)(r.send_lo - g.zlo) * g.cplane, f + (size_t)(r.recv_lo - g.zlo) * g.cplane,
+                           (size_t)r.send_n * g.cplane * sizeof(float), (size_t)r.recv_n * g.cplane * sizeof(float)});
+        }
+    }
+    s->exchanges++;
+    if (s->exchange(s->exchange_ctx, set, out.data(), (int)out.size(), (void*)s->stream) != 0)
+        return fail(s, SMK_ERR_TRANSPORT, "halo transport callback failed");
+    return SMK_OK;
+}
+
+int exec_op(smk_sim* s, const slab::Op& op, float dt)
+{
+    switch (op.kind) {
+    case slab::OP_FLIP: flip(s); return SMK_OK;
+    case slab::OP_FILL: return stage_fill(s);
+    case slab::OP_FORCE: return stage_force_clamp(s, dt, op.a, op.b);
+    case slab::OP_PRESSURE: {
+        Span sp(s, SMK_STAGE_PRESSURE);
+        int rc = run_pressure_pass(s, op.p0, op.p1);
+        if (rc == SMK_OK) CK(s, cudaGetLastError());
+        return rc;
+    }
+    case slab::OP_ADVECT_VEL: return stage_advect_velocity(s, dt, op.a, op.b, op.p0, op.p1);
+    case slab::OP_ADVECT_SMOKE: return stage_advect_smoke(s, dt, op.a, op.b, op.p0, op.p1);
+    case slab::OP_EXCHANGE: return run_exchange(s, op.a);
+    }
+    return fail(s, SMK_ERR_ARG, "unknown op kind");
+}
+
+// one step = the plan of slab_plan.h executed with CUDA kernels (a single GPU is the 1-slab case: no exchanges)
 int enqueue_step(smk_sim* s, float dt, float* density_host)
 {
-    int rc;
-    flip(s);
-    if ((rc = stage_fill(s))) return rc;
-    if ((rc = stage_force_clamp(s, dt))) return rc;
-    if ((rc = stage_pressure(s))) return rc;
-    if ((rc = stage_advect_velocity(s, dt))) return rc;
-    if ((rc = stage_advect_smoke(s, dt))) return rc;
-    if (density_host) {
+    int rc = SMK_OK;
+    const std::vector<slab::Op> ops = slab::plan_step(s->geom, s->iterations, effective_fuse(s), s->carry);
+    for (size_t i = 0; i < ops.size() && rc == SMK_OK; i++) rc = exec_op(s, ops[i], dt);
+    if (rc) return rc;
+    if (density_host) { // this slab's OWNED planes of the new density (a single GPU owns everything)
         Span sp(s, SMK_STAGE_READBACK);
-        const size_t bytes = cell_count(s->g) * sizeof(float);
-        float* dst = density_host + (size_t)s->g.zlo * s->g.cplane;
+        const GridP& g = s->g;
+        const size_t bytes = (size_t)(s->geom.c1 - s->geom.c0) * g.cplane * sizeof(float);
+        float* dst = density_host + (size_t)s->geom.c0 * g.cplane;
         try_register(s, dst, bytes);
-        CK(s, cudaMemcpyAsync(dst, s->smoke[s->past], bytes, cudaMemcpyDeviceToHost, s->stream));
+        CK(s, cudaMemcpyAsync(dst, s->smoke[s->past] + (size_t)(s->geom.c0 - g.zlo) * g.cplane, bytes, cudaMemcpyDeviceToHost,
+                              s->stream));
     }
     return SMK_OK;
 }
@@ -430,6 +484,7 @@ struct FieldRef {
     void* dev;
     size_t elem;
     bool staggered;
+    bool is_mask;
 };
 
 int field_ref(smk_sim* s, int field, int which, FieldRef* out)
@@ -437,11 +492,11 @@ int field_ref(smk_sim* s, int field, int which, FieldRef* out)
     if (which < 0 || which > 3) return SMK_ERR_ARG;
     const int b = which == SMK_BUF_NOW ? s->now : which == SMK_BUF_PAST ? s->past : which - 2;
     switch (field) {
-    case SMK_FIELD_SMOKE: *out = {s->smoke[b], 4, false}; return SMK_OK;
-    case SMK_FIELD_U: *out = {s->u[b], 4, true}; return SMK_OK;
-    case SMK_FIELD_V: *out = {s->v[b], 4, true}; return SMK_OK;
-    case SMK_FIELD_W: *out = {s->w[b], 4, true}; return SMK_OK;
-    case SMK_FIELD_MASK: *out = {s->mask, 1, false}; return SMK_OK;
+    case SMK_FIELD_SMOKE: *out = {s->smoke[b], 4, false, false}; return SMK_OK;
+    case SMK_FIELD_U: *out = {s->u[b], 4, true, false}; return SMK_OK;
+    case SMK_FIELD_V: *out = {s->v[b], 4, true, false}; return SMK_OK;
+    case SMK_FIELD_W: *out = {s->w[b], 4, true, false}; return SMK_OK;
+    case SMK_FIELD_MASK: *out = {s->mask, 1, false, true}; return SMK_OK;
     }
     return SMK_ERR_ARG;
 }
@@ -461,12 +516,13 @@ int copy_field(smk_sim* s, const FieldRef& f, void* host, bool to_host)
         p.extent = make_cudaExtent(hx * f.elem, hy, (size_t)g.nzn);
     } else {
         const size_t hx = (size_t)g.W, hy = (size_t)g.H;
-        char* hbase = (char*)host + (size_t)g.zlo * hx * hy * f.elem;
+        const int z0 = f.is_mask ? g.mzlo : g.zlo, nz = f.is_mask ? g.nzm : g.nzc;
+        char* hbase = (char*)host + (size_t)z0 * hx * hy * f.elem;
         cudaPitchedPtr hp = make_cudaPitchedPtr(hbase, hx * f.elem, hx, hy);
         cudaPitchedPtr dp = make_cudaPitchedPtr(f.dev, hx * f.elem, hx, hy);
         p.srcPtr = to_host ? dp : hp;
         p.dstPtr = to_host ? hp : dp;
-        p.extent = make_cudaExtent(hx * f.elem, hy, (size_t)g.nzc);
+        p.extent = make_cudaExtent(hx * f.elem, hy, (size_t)nz);
     }
     p.kind = to_host ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
     CK(s, cudaMemcpy3DAsync(&p, s->stream));
@@ -474,12 +530,14 @@ int copy_field(smk_sim* s, const FieldRef& f, void* host, bool to_host)
     return SMK_OK;
 }
 
-int create_common(smk_sim** out, unsigned W, unsigned H, unsigned D, int c0, int c1, int ghost, const float* smoke0_full)
+int create_common(smk_sim** out, unsigned W, unsigned H, unsigned D, int rank, int world, int ghost, const float* smoke0_full)
 {
     if (!out) return SMK_ERR_ARG;
     *out = nullptr;
     if (W < 3 || H < 3 || D < 3 || W > 4096 || H > 4096 || D > 65535) return fail(nullptr, SMK_ERR_ARG, "grid dimensions out of range");
-    if (c0 < 0 || c1 > (int)D || c0 >= c1) return fail(nullptr, SMK_ERR_ARG, "bad slab range");
+    if (world < 1 || rank < 0 || rank >= world) return fail(nullptr, SMK_ERR_ARG, "bad rank / world size");
+    const slab::Geom geom = slab::make_geom((int)W, (int)H, (int)D, world, rank, ghost);
+    if (!slab::geom_ok(geom)) return fail(nullptr, SMK_ERR_ARG, "slab too thin for its ghost depth (need D/world >= ghost+1, ghost >= 4)");
     smk_sim* s = new smk_sim;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -495,11 +553,13 @@ int create_common(smk_sim** out, unsigned W, unsigned H, unsigned D, int c0, int
     g.SY = (int)H + 1;
     g.nplane = (long long)g.P * g.SY;
     g.cplane = (long long)W * H;
-    s->c0 = c0; s->c1 = c1; s->ghost = ghost;
-    g.zlo = std::max(0, c0 - ghost);
-    const int zhc = std::min((int)D, c1 + ghost);
-    g.nzc = zhc - g.zlo;
+    s->geom = geom;
+    s->carry = slab::initial_carry(geom);
+    g.zlo = geom.zlo;
+    g.nzc = geom.zhc - geom.zlo;
     g.nzn = g.nzc + 1;
+    g.mzlo = std::max(0, geom.zlo - (geom.has_lower() ? 1 : 0));
+    g.nzm = std::min((int)D, geom.zhc + (geom.has_upper() ? 1 : 0)) - g.mzlo;
     g.PC = (int)((W + 15) / 16 * 16);
     g.kplane = (long long)g.PC * g.H;
     cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -527,13 +587,16 @@ int create_common(smk_sim** out, unsigned W, unsigned H, unsigned D, int c0, int
         CKN(cudaMemsetAsync(s->v[i], 0, nb, s->stream));
         CKN(cudaMemsetAsync(s->w[i], 0, nb, s->stream));
     }
-    CKN(cudaMalloc(&s->mask, cell_count(g)));
+    const size_t mask_bytes = (size_t)g.cplane * g.nzm;
+    CKN(cudaMalloc(&s->mask, mask_bytes));
+    CKN(cudaMalloc(&s->d_flags, 64));
+    CKN(cudaMemsetAsync(s->d_flags, 0, 64, s->stream));
     CKN(cudaMalloc(&s->code, code_count(g)));
     CKN(cudaMalloc(&s->d_scalar, 64));
     CKN(cudaMemsetAsync(s->code, 0, code_count(g), s->stream));
     // mask: fluid everywhere, solid on the plane y == 0 (cu:200-207)
-    CKN(cudaMemsetAsync(s->mask, 1, cell_count(g), s->stream));
-    CKN(cudaMemset2DAsync(s->mask, (size_t)g.cplane, 0, (size_t)g.W, (size_t)g.nzc, s->stream));
+    CKN(cudaMemsetAsync(s->mask, 1, mask_bytes, s->stream));
+    CKN(cudaMemset2DAsync(s->mask, (size_t)g.cplane, 0, (size_t)g.W, (size_t)g.nzm, s->stream));
     if (smoke0_full)
         CKN(cudaMemcpyAsync(s->smoke[0], smoke0_full + (size_t)g.zlo * g.cplane, cb, cudaMemcpyHostToDevice, s->stream));
     CKN(cudaStreamSynchronize(s->stream));
@@ -553,13 +616,50 @@ const char* smk_last_error(smk_sim* s) { return s ? s->err.c_str() : g_last_glob
 
 int smk_create(smk_sim** out, unsigned W, unsigned H, unsigned D, const float* smoke0_host)
 {
-    return create_common(out, W, H, D, 0, (int)D, 0, smoke0_host);
+    return create_common(out, W, H, D, 0, 1, 0, smoke0_host);
 }
 
-int smk_create_slab(smk_sim** out, unsigned W, unsigned H, unsigned D, unsigned z_begin, unsigned z_end, unsigned ghost,
+int smk_create_slab(smk_sim** out, unsigned W, unsigned H, unsigned D, unsigned rank, unsigned world, unsigned ghost,
                     const float* smoke0_host_full)
 {
-    return create_common(out, W, H, D, (int)z_begin, (int)z_end, (int)ghost, smoke0_host_full);
+    return create_common(out, W, H, D, (int)rank, (int)world, (int)ghost, smoke0_host_full);
+}
+
+// host-only helpers (no CUDA): the slab geometry and the schedule of one step, as executed by smk_step
+int smk_slab_geometry(unsigned W, unsigned H, unsigned D, unsigned world, unsigned rank, unsigned ghost, int* out8)
+{
+    if (!out8 || world < 1 || rank >= world) return SMK_ERR_ARG;
+    const slab::Geom g = slab::make_geom((int)W, (int)H, (int)D, (int)world, (int)rank, (int)ghost);
+    out8[0] = g.c0; out8[1] = g.c1; out8[2] = g.zlo; out8[3] = g.zhc; out8[4] = g.ghost; out8[5] = slab::geom_ok(g) ? 1 : 0;
+    out8[6] = g.own_node_lo(); out8[7] = g.own_node_hi();
+    return SMK_OK;
+}
+
+int smk_slab_plan(unsigned W, unsigned H, unsigned D, unsigned world, unsigned rank, unsigned ghost, int iterations, int fuse,
+                  int steps, int* ops5, int max_ops)
+{
+    if (world < 1 || rank >= world || steps < 1) return -SMK_ERR_ARG;
+    const slab::Geom g = slab::make_geom((int)W, (int)H, (int)D, (int)world, (int)rank, (int)ghost);
+    slab::Carry carry = slab::initial_carry(g);
+    int n = 0;
+    for (int st = 0; st < steps; st++)
+        for (const slab::Op& op : slab::plan_step(g, iterations, fuse, carry)) {
+            if (ops5 && n < max_ops) { int* o = ops5 + 5 * n; o[0] = op.kind; o[1] = op.a; o[2] = op.b; o[3] = op.p0; o[4] = op.p1; }
+            n++;
+        }
+    return n;
+}
+
+int smk_slab_regions(unsigned W, unsigned H, unsigned D, unsigned world, unsigned rank, unsigned ghost, int set, int* out5, int max_regions)
+{
+    if (world < 1 || rank >= world) return -SMK_ERR_ARG;
+    const slab::Geom g = slab::make_geom((int)W, (int)H, (int)D, (int)world, (int)rank, (int)ghost);
+    int n = 0;
+    for (const slab::Region& r : slab::regions(g, set)) {
+        if (out5 && n < max_regions) { int* o = out5 + 5 * n; o[0] = r.side; o[1] = r.send_lo; o[2] = r.send_n; o[3] = r.recv_lo; o[4] = r.recv_n; }
+        n++;
+    }
+    return n;
 }
 
 int smk_destroy(smk_sim* s)
@@ -573,7 +673,7 @@ int smk_destroy(smk_sim* s)
         cudaFree(s->smoke[i]); cudaFree(s->u[i]); cudaFree(s->v[i]); cudaFree(s->w[i]);
     }
     for (int i = 0; i < 3; i++) cudaFree(s->scratch[i]);
-    cudaFree(s->mask); cudaFree(s->code); cudaFree(s->d_scalar);
+    cudaFree(s->mask); cudaFree(s->code); cudaFree(s->d_scalar); cudaFree(s->d_flags);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     cudaGetLastError();
     delete s;
@@ -666,6 +766,14 @@ int smk_sync(smk_sim* s)
 {
     if (!s) return SMK_ERR_ARG;
     CK(s, cudaStreamSynchronize(s->stream));
+    if (s->geom.world > 1) { // slab runs: did a backtrace leave the valid planes?
+        int flag = 0;
+        CK(s, cudaMemcpy(&flag, s->d_flags, sizeof(int), cudaMemcpyDeviceToHost));
+        if (flag) {
+            cudaMemset(s->d_flags, 0, sizeof(int));
+            return fail(s, SMK_ERR_REACH, "a backtrace reached beyond the slab's valid ghost planes (|w|*dt >= 1 cell): increase ghost");
+        }
+    }
     if (s->spans.size() > 4096) return fold_timers(s);
     return SMK_OK;
 }
@@ -682,7 +790,7 @@ const float* smk_density_device(smk_sim* s) { return s ? s->smoke[s->past] : nul
 
 int smk_stage_flip(smk_sim* s) { if (!s) return SMK_ERR_ARG; flip(s); return SMK_OK; }
 int smk_stage_fill(smk_sim* s) { return s ? stage_fill(s) : SMK_ERR_ARG; }
-int smk_stage_force_clamp(smk_sim* s, float dt) { return s ? stage_force_clamp(s, dt) : SMK_ERR_ARG; }
+int smk_stage_force_clamp(smk_sim* s, float dt) { return s ? stage_force_clamp(s, dt, s->g.zlo, s->g.zlo + s->g.nzn) : SMK_ERR_ARG; }
 int smk_stage_pressure_halfsweep(smk_sim* s, int offset)
 {
     if (!s) return SMK_ERR_ARG;
@@ -692,8 +800,8 @@ int smk_stage_pressure_halfsweep(smk_sim* s, int offset)
     return SMK_OK;
 }
 int smk_stage_pressure(smk_sim* s) { return s ? stage_pressure(s) : SMK_ERR_ARG; }
-int smk_stage_advect_velocity(smk_sim* s, float dt) { return s ? stage_advect_velocity(s, dt) : SMK_ERR_ARG; }
-int smk_stage_advect_smoke(smk_sim* s, float dt) { return s ? stage_advect_smoke(s, dt) : SMK_ERR_ARG; }
+int smk_stage_advect_velocity(smk_sim* s, float dt) { return s ? stage_advect_velocity(s, dt, s->g.zlo, s->g.zlo + s->g.nzn, s->g.zlo, s->g.zlo + s->g.nzn - 1) : SMK_ERR_ARG; }
+int smk_stage_advect_smoke(smk_sim* s, float dt) { return s ? stage_advect_smoke(s, dt, s->g.zlo, s->g.zlo + s->g.nzc, s->g.zlo, s->g.zlo + s->g.nzc - 1) : SMK_ERR_ARG; }
 
 int smk_get_field(smk_sim* s, int field, int which, void* host_dst)
 {
@@ -710,6 +818,7 @@ int smk_set_field(smk_sim* s, int field, int which, const void* host_src)
     if (field_ref(s, field, which, &f)) return fail(s, SMK_ERR_ARG, "bad field / buffer selector");
     int rc = copy_field(s, f, const_cast<void*>(host_src), false);
     if (rc) return rc;
+    s->carry = slab::initial_carry(s->geom); // injected fields are full-size on every rank: all stored planes valid
     if (field == SMK_FIELD_MASK) { // keep the stencil codes consistent with an injected mask
         const GridP& g = s->g;
         smk::k_codes<<<row_grid(g.cplane, g.nzc), 256, 0, s->stream>>>(g, s->mask, s->code, g.zlo);
@@ -721,6 +830,12 @@ int smk_set_field(smk_sim* s, int field, int which, const void* host_src)
 }
 
 int smk_index_now(smk_sim* s) { return s ? s->now : -1; }
+
+int smk_exec_op(smk_sim* s, const int* op5, float dt)
+{
+    if (!s || !op5) return SMK_ERR_ARG;
+    return exec_op(s, slab::Op{op5[0], op5[1], op5[2], op5[3], op5[4]}, dt);
+}
 
 int smk_max_divergence(smk_sim* s, float* out)
 {
