@@ -174,17 +174,31 @@ def time_cpu(scene, budget_s, steps=None, warmup=0):
     return W * H * Ds * steps / dt, cores, kind, sample, dt / steps * 1e3
 
 
+def extended_scene(scene, label, world, explicit_workload):
+    """N > 1 without an explicit workload: weak scaling (BASELINE configs[4] pattern) -- every GPU keeps the N=1 workload
+    as its slab, the domain grows along z; source / obstacle keep their coordinates."""
+    W, H, D = scene[:3]
+    if world > 1 and not explicit_workload:
+        D = D * world
+        scene = (W, H, D) + tuple(scene[3:])
+        label += f", extended to {W}x{H}x{D}: {world} z-slabs of {D // world} planes (weak scaling)"
+    return scene, label
+
+
 def run_reference_arm(args, rank, world):
+    """The reference's own CPU implementation of the path on the host cores, same config / metric / unit as the b200 arm.
+    Under torchrun only rank 0 works; the other ranks exit 0."""
     if rank != 0:
         return
     wname, scene, label = parse_workload(args.workload, args.gpus)
+    scene, label = extended_scene(scene, label, max(world, args.gpus), args.workload is not None)
     val, cores, kind, sample, ms = time_cpu(scene, budget_s=150.0, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": label + "; reference schedule RBGS omega=1.9 x30; CPU implementation of the reference step",
-                   "solver": "rbgs", "iterations": 30},
+        "config": {"workload": label + "; reference schedule RBGS omega=1.9 x30; the reference's kernel bodies as an OpenMP host loop",
+                   "grid": list(scene[:3]), "solver": "rbgs", "iterations": 30},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -226,12 +240,8 @@ def main():
 
     wname, scene, label = parse_workload(args.workload, args.gpus)
     W, H, D = scene[:3]
-    if world > 1 and args.workload is None:
-        # weak scaling (BASELINE configs[4] pattern): every GPU keeps the N=1 workload as its slab, the domain grows
-        # along z; source / obstacle keep their coordinates (plume in slab 0, the work per cell is data independent)
-        D = D * world
-        scene = (W, H, D) + tuple(scene[3:])
-        label += f", extended to {W}x{H}x{D}: {world} z-slabs of {D // world} planes (weak scaling)"
+    scene, label = extended_scene(scene, label, world, args.workload is not None)
+    W, H, D = scene[:3]
     # the library runs the whole step on ONE stream; hand it a real (non-default) torch stream so that
     # torch.cuda.Event brackets exactly the work of the step and the NCCL halo traffic is ordered on it
     stream = torch.cuda.Stream()
@@ -241,6 +251,8 @@ def main():
     if world > 1:
         sim = smk.SmokeSim(W, H, D, slab=(rank, world), ghost=args.ghost)
         transport = smk.slab.TorchTransport(rank, world)
+        if os.environ.get("SMK_BENCH_NULL_TRANSPORT"):   # diagnosis only: skip the halo traffic (results are wrong)
+            transport.__class__ = type("NullTransport", (smk.slab.TorchTransport,), {"__call__": lambda self, s, r, st: setattr(self, "exchanges", self.exchanges + 1) or 0})
         sim.set_exchange(transport)
     else:
         sim = smk.SmokeSim(W, H, D)

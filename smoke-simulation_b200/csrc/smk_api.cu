@@ -173,6 +173,16 @@ ObjP pack_objects(const smk_sim* s)
 
 // ---- stages (global plane ranges; a single GPU passes the whole stored range) -------------------------------
 
+void launch_codes(smk_sim* s)
+{
+    const GridP& g = s->g;
+    if ((g.W & 3) == 0)
+        smk::k_codes4<<<row_grid(g.cplane / 4, g.nzc), 256, 0, s->stream>>>(g, s->mask, s->code, g.zlo);
+    else
+        smk::k_codes<<<row_grid(g.cplane, g.nzc), 256, 0, s->stream>>>(g, s->mask, s->code, g.zlo);
+    count_launch(s, SMK_STAGE_FILL);
+}
+
 int stage_fill(smk_sim* s)
 {
     const GridP& g = s->g;
@@ -183,8 +193,7 @@ int stage_fill(smk_sim* s)
             smk::k_fill<<<row_grid(g.cplane, g.nzm), 256, 0, s->stream>>>(g, s->smoke[0], s->smoke[1], s->mask, o, g.mzlo);
             count_launch(s, SMK_STAGE_FILL);
         }
-        smk::k_codes<<<row_grid(g.cplane, g.nzc), 256, 0, s->stream>>>(g, s->mask, s->code, g.zlo);
-        count_launch(s, SMK_STAGE_FILL);
+        launch_codes(s);
     }
     CK(s, cudaGetLastError());
     return SMK_OK;
@@ -371,8 +380,10 @@ int stage_advect_velocity(smk_sim* s, float dt, int za, int zb, int vlo, int vhi
     za = std::max(za, std::max(1, g.zlo));
     zb = std::min(zb, std::min(g.D, g.zlo + g.nzc));
     if (zb > za) {
-        smk::k_advect_velocity<<<row_grid(g.nplane, zb - za), 256, 0, s->stream>>>(
-            g, s->u[n], s->v[n], s->w[n], s->u[p], s->v[p], s->w[p], s->code, dt, za, make_int2(vlo, vhi), s->d_flags);
+        static const int by = getenv("SMK_ADV_BY") ? atoi(getenv("SMK_ADV_BY")) : 4, bz = getenv("SMK_ADV_BZ") ? atoi(getenv("SMK_ADV_BZ")) : 2;
+        const dim3 blk(32, by, bz), grd((g.W + 31) / 32, (g.H + by - 1) / by, (zb - za + bz - 1) / bz);
+        smk::k_advect_velocity<<<grd, blk, 0, s->stream>>>(
+            g, s->u[n], s->v[n], s->w[n], s->u[p], s->v[p], s->w[p], s->code, dt, za, zb, make_int2(vlo, vhi), s->d_flags);
         count_launch(s, SMK_STAGE_ADVECT_VEL);
     }
     CK(s, cudaGetLastError());
@@ -388,8 +399,10 @@ int stage_advect_smoke(smk_sim* s, float dt, int za, int zb, int vlo, int vhi)
     za = std::max(za, std::max(1, g.zlo));
     zb = std::min(zb, std::min(g.D - 1, g.zlo + g.nzc));
     if (zb > za) {
-        smk::k_advect_smoke<<<row_grid(g.cplane, zb - za), 256, 0, s->stream>>>(
-            g, s->smoke[n], s->smoke[p], s->u[p], s->v[p], s->w[p], s->code, dt, za, make_int2(vlo, vhi), s->d_flags);
+        static const int by = getenv("SMK_ADV_BY") ? atoi(getenv("SMK_ADV_BY")) : 4, bz = getenv("SMK_ADV_BZ") ? atoi(getenv("SMK_ADV_BZ")) : 2;
+        const dim3 blk(32, by, bz), grd((g.W + 31) / 32, (g.H + by - 1) / by, (zb - za + bz - 1) / bz);
+        smk::k_advect_smoke<<<grd, blk, 0, s->stream>>>(
+            g, s->smoke[n], s->smoke[p], s->u[p], s->v[p], s->w[p], s->code, dt, za, zb, make_int2(vlo, vhi), s->d_flags);
         count_launch(s, SMK_STAGE_ADVECT_SMOKE);
     }
     CK(s, cudaGetLastError());
@@ -821,8 +834,7 @@ int smk_set_field(smk_sim* s, int field, int which, const void* host_src)
     s->carry = slab::initial_carry(s->geom); // injected fields are full-size on every rank: all stored planes valid
     if (field == SMK_FIELD_MASK) { // keep the stencil codes consistent with an injected mask
         const GridP& g = s->g;
-        smk::k_codes<<<row_grid(g.cplane, g.nzc), 256, 0, s->stream>>>(g, s->mask, s->code, g.zlo);
-        count_launch(s, SMK_STAGE_FILL);
+        launch_codes(s);
         CK(s, cudaGetLastError());
         CK(s, cudaStreamSynchronize(s->stream));
     }
