@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--workload", default=None, help="C1|C2|C3|C4 or NxNxN (default: C2; N>1: C2 extended along z, weak scaling)")
     ap.add_argument("--fuse", type=int, default=0, help="half-sweeps fused per pressure launch (0 = library default)")
     ap.add_argument("--ghost", type=int, default=8, help="ghost planes per interior slab side (multi-GPU)")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="multi-GPU halo transport")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -250,10 +251,11 @@ def main():
     transport = None
     if world > 1:
         sim = smk.SmokeSim(W, H, D, slab=(rank, world), ghost=args.ghost)
-        transport = smk.slab.TorchTransport(rank, world)
-        if os.environ.get("SMK_BENCH_NULL_TRANSPORT"):   # diagnosis only: skip the halo traffic (results are wrong)
-            transport.__class__ = type("NullTransport", (smk.slab.TorchTransport,), {"__call__": lambda self, s, r, st: setattr(self, "exchanges", self.exchanges + 1) or 0})
-        sim.set_exchange(transport)
+        if args.transport == "p2p":     # peer-mapped memory over NVLink (CUDA IPC): no Python, no NCCL in the step
+            smk.slab.attach_peers_ipc(sim, rank, world, dist, torch.device("cuda", local_rank))
+        else:                           # torch.distributed send/recv (NCCL) through the transport callback
+            transport = smk.slab.TorchTransport(rank, world)
+            sim.set_exchange(transport)
     else:
         sim = smk.SmokeSim(W, H, D)
     po.setup_scene(sim, scene)
@@ -277,7 +279,7 @@ def main():
     # ---- timed region 1: device-resident throughput ("value") ------------------------------------------------
     sim.reset_timers()
     l0 = sim.launch_count()
-    x0 = transport.exchanges if transport else 0
+    x0 = sim.exchange_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         barrier()
@@ -288,7 +290,7 @@ def main():
         barrier()
     ms = e0.elapsed_time(e1)
     launches = sim.launch_count() - l0
-    exchanges = (transport.exchanges - x0) if transport else 0
+    exchanges = sim.exchange_count() - x0
     times = sim.stage_times()
     if world > 1:
         t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
@@ -343,6 +345,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": label + "; reference schedule RBGS omega=1.9 x30", "grid": [W, H, D], "solver": "rbgs",
                        "iterations": 30, "fuse": args.fuse, "parallelism": f"zslab{world}", "ghost": args.ghost if world > 1 else 0,
+                       "transport": (args.transport if world > 1 else None),
                        "halo_exchanges_per_step": exchanges / K,
                        "l2": f"state per GPU {(2 * cells_local * 4 + 9 * (W + 1) * (H + 1) * (c1 - c0 + 1) * 4 + 2 * cells_local) / 1e6:.0f} MB "
                              "(> 126 MB L2): inputs larger than L2, no explicit flush"},

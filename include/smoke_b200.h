@@ -172,6 +172,23 @@ typedef struct {
 typedef int (*smk_exchange_fn)(void* ctx, int set, const smk_halo_region* regions, int nregions, void* cuda_stream);
 int smk_set_exchange(smk_sim* s, smk_exchange_fn fn, void* ctx);
 
+/* Peer-memory halo path (the B200-native transport): every slab's exchanged fields live in one allocation ("arena").
+ * A neighbour process maps it through a 64-byte CUDA IPC handle (smk_p2p_export -> smk_p2p_attach_ipc); slabs that
+ * live in one process pass the arena pointer (smk_p2p_arena -> smk_p2p_attach_ptr).  Once every existing neighbour is
+ * attached, smk_step needs no transport callback: the fused pressure passes read the neighbours' boundary planes
+ * directly over NVLink inside the kernel (one epoch handshake per pass, no ghost copies), and the remaining halo
+ * refreshes (before advection) are pulls over the mapped memory.  side: 0 = lower-z neighbour, 1 = upper-z. */
+int smk_p2p_export(smk_sim* s, unsigned char* handle64);
+int smk_p2p_attach_ipc(smk_sim* s, int side, const unsigned char* handle64);
+void* smk_p2p_arena(smk_sim* s);
+int smk_p2p_attach_ptr(smk_sim* s, int side, void* peer_arena);
+long smk_exchange_count(smk_sim* s);
+/* test helper for several slabs driven by ONE host thread on ONE GPU: publish the next epoch without waiting */
+int smk_p2p_presignal(smk_sim* s);
+/* like smk_slab_plan, for the peer-memory path (pressure passes consume no ghost depth) */
+int smk_slab_plan_p2p(unsigned W, unsigned H, unsigned D, unsigned world, unsigned rank, unsigned ghost, int iterations,
+                      int fuse, int steps, int* ops5, int max_ops);
+
 /* execute ONE operation of a plan returned by smk_slab_plan (op5 = {kind, a, b, p0, p1}); an exchange op calls the
  * transport.  smk_step == every op of plan_step in order.  Used by tests to drive several slabs in lock-step. */
 int smk_exec_op(smk_sim* s, const int* op5, float dt);

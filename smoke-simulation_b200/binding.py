@@ -97,6 +97,15 @@ def load_library():
     L.smk_launch_count.restype = C.c_long
     L.smk_set_exchange.argtypes = [_vp, EXCHANGE_FN, _vp]
     L.smk_exec_op.argtypes = [_vp, C.POINTER(_i), _f]
+    L.smk_p2p_export.argtypes = [_vp, C.c_char_p]
+    L.smk_p2p_attach_ipc.argtypes = [_vp, _i, C.c_char_p]
+    L.smk_p2p_arena.argtypes = [_vp]
+    L.smk_p2p_arena.restype = _vp
+    L.smk_p2p_attach_ptr.argtypes = [_vp, _i, _vp]
+    L.smk_p2p_presignal.argtypes = [_vp]
+    L.smk_exchange_count.argtypes = [_vp]
+    L.smk_exchange_count.restype = C.c_long
+    L.smk_slab_plan_p2p.argtypes = [C.c_uint] * 6 + [_i, _i, _i, C.POINTER(_i), _i]
     L.smk_last_error.argtypes = [_vp]
     L.smk_last_error.restype = C.c_char_p
     _lib = L
@@ -236,6 +245,19 @@ class SmokeSim:
         kind = OP_NAMES.index(op[0]) if isinstance(op[0], str) else int(op[0])
         arr = (_i * 5)(kind, *[int(v) for v in op[1:5]])
         self._ck(self.L.smk_exec_op(self.h, arr, dt))
+
+    # -- peer-memory halo path
+    def p2p_export(self):
+        """64-byte CUDA IPC handle of this slab's arena (send it to the neighbour processes)."""
+        buf = C.create_string_buffer(64)
+        self._ck(self.L.smk_p2p_export(self.h, buf))
+        return buf.raw
+
+    def p2p_attach_ipc(self, side, handle): self._ck(self.L.smk_p2p_attach_ipc(self.h, side, bytes(handle)))
+    def p2p_arena(self): return self.L.smk_p2p_arena(self.h)
+    def p2p_attach_ptr(self, side, ptr): self._ck(self.L.smk_p2p_attach_ptr(self.h, side, ptr))
+    def exchange_count(self): return int(self.L.smk_exchange_count(self.h))
+    def p2p_presignal(self): self._ck(self.L.smk_p2p_presignal(self.h))
 
     def set_exchange(self, pyfunc):
         """pyfunc(set_id, [(side, send_ptr, recv_ptr, send_bytes, recv_bytes), ...], stream_ptr) -> int"""

@@ -482,4 +482,42 @@ __global__ void __launch_bounds__(256) k_max_divergence(GridP g, const float* __
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Cross-GPU synchronisation for the peer-memory halo path: monotonically increasing epoch counters that live in
+// each slab's arena and are written by its neighbours over NVLink.
+//   k_epoch_signal: after everything enqueued before it on the stream (kernel boundary + system fence), publish
+//                   `epoch` into the neighbour's counter  => "my planes are final for this epoch and I no longer read
+//                   yours from the previous one"
+//   k_epoch_wait:   spin until the neighbour published `epoch`; a clock-based timeout raises flag[1] instead of
+//                   hanging the GPU if a peer died.
+__global__ void k_epoch_signal(unsigned* peer_counter_a, unsigned* peer_counter_b, unsigned epoch)
+{
+    __threadfence_system();
+    if (peer_counter_a) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_counter_a), "r"(epoch) : "memory");
+    if (peer_counter_b) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_counter_b), "r"(epoch) : "memory");
+}
+
+__global__ void k_epoch_wait(const unsigned* my_counter_a, const unsigned* my_counter_b, unsigned epoch, int* flags,
+                             long long timeout_cycles)
+{
+    const long long t0 = clock64();
+    for (int i = 0; i < 2; i++) {
+        const unsigned* c = i == 0 ? my_counter_a : my_counter_b;
+        if (!c) continue;
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(c) : "memory");
+            if ((int)(v - epoch) >= 0) break;
+            if (clock64() - t0 > timeout_cycles) { flags[1] = 1; return; }
+            __nanosleep(200);
+        } while (true);
+    }
+}
+
+// contiguous plane ranges pulled from a neighbour's memory (or any device memory): 16-byte grid-stride copy
+__global__ void __launch_bounds__(256) k_copy16(float4* __restrict__ dst, const float4* __restrict__ src, size_t n16)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 } // namespace smk

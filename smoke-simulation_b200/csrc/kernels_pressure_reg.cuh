@@ -129,11 +129,24 @@ __device__ __forceinline__ void reg_update(float2& ue, float2& uo, float2& we, f
     }
 }
 
+// Where the planes outside the slab's OWNED range come from in a multi-GPU run: directly from the neighbour's memory
+// (peer-mapped over NVLink), i.e. the halo transfer is fused into the pressure pass plane by plane -- no ghost copy,
+// no separate exchange.  u == nullptr: no neighbour on that side / single GPU (planes come from the local arrays).
+struct PeerPlanes {
+    const float* u; const float* v; const float* w; // the neighbour's current "in" buffers
+    int zlo;                                         // global index of the neighbour's first stored plane
+};
+struct PassRange {
+    int out_lo, out_hi;  // node planes this launch writes: [out_lo, out_hi)
+    int own_lo, own_hi;  // node planes owned by this slab (inclusive); outside them a peer is the source if present
+    PeerPlanes lower, upper;
+};
+
 template <int K, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ vi, const float* __restrict__ wi,
                float* __restrict__ uo, float* __restrict__ vo, float* __restrict__ wo,
-               const unsigned char* __restrict__ code, int sweep0, int zchunk)
+               const unsigned char* __restrict__ code, int sweep0, int zchunk, PassRange pr)
 {
     using C = RegCfg<K, NW>;
     constexpr int LY = C::LY, RS = C::RS, HO = C::HO, R = C::R, PLS = C::PLS;
@@ -146,8 +159,8 @@ k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ 
     const int yl = wid + (lane >> 4) * NW;                   // this half-warp's row
     const int x0 = blockIdx.x * C::OX - K;
     const int y0 = blockIdx.y * C::OY - K;
-    const int zo0 = g.zlo + blockIdx.z * zchunk;             // output node planes [zo0, zo1)
-    const int zo1 = min(zo0 + zchunk, g.zlo + g.nzn);
+    const int zo0 = pr.out_lo + blockIdx.z * zchunk;         // output node planes [zo0, zo1)
+    const int zo1 = min(zo0 + zchunk, pr.out_hi);
     const int t0 = zo0 - K, t1 = zo1 + K - 1;                // planes that enter the ring
     const int xg = x0 + 4 * h, yg = y0 + yl;
 
@@ -174,15 +187,20 @@ k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ 
     float4 pu, pv, pw;
     unsigned pc;
     auto prefetch = [&](int z) {
-        const bool zn = z >= g.zlo && z < g.zlo + g.nzn;
+        // source of plane z: the local arrays, or a neighbour's memory for planes outside the owned range
+        const float *su = ui, *sv_ = vi, *sw = wi;
+        int szlo = g.zlo;
+        bool zn = z >= g.zlo && z < g.zlo + g.nzn;
+        if (z < pr.own_lo && pr.lower.u) { su = pr.lower.u; sv_ = pr.lower.v; sw = pr.lower.w; szlo = pr.lower.zlo; zn = z >= szlo; }
+        else if (z > pr.own_hi && pr.upper.u) { su = pr.upper.u; sv_ = pr.upper.v; sw = pr.upper.w; szlo = pr.upper.zlo; zn = z <= g.D; }
         const bool zc = z >= g.zlo && z < g.zlo + g.nzc;
         pu = pv = pw = make_float4(0.f, 0.f, 0.f, 0.f);
         pc = 0;
         if (zn && nok) {
-            const long long n = (long long)(z - g.zlo) * g.nplane + noff;
-            pu = __ldg(reinterpret_cast<const float4*>(ui + n));
-            pv = __ldg(reinterpret_cast<const float4*>(vi + n));
-            pw = __ldg(reinterpret_cast<const float4*>(wi + n));
+            const long long n = (long long)(z - szlo) * g.nplane + noff;
+            pu = __ldg(reinterpret_cast<const float4*>(su + n));
+            pv = __ldg(reinterpret_cast<const float4*>(sv_ + n));
+            pw = __ldg(reinterpret_cast<const float4*>(sw + n));
         }
         if (zc && kok) pc = __ldg(reinterpret_cast<const unsigned*>(code + (long long)(z - g.zlo) * g.kplane + koff));
     };

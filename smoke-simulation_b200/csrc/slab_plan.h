@@ -94,7 +94,10 @@ inline std::vector<Region> regions(const Geom& g, int set)
 }
 
 // The schedule of ONE step (cu:774-819) on one slab.  `fuse` = half-sweeps per pressure pass (1, 2 or 4).
-inline std::vector<Op> plan_step(const Geom& g, int iterations, int fuse, Carry& carry)
+// `peer_passes`: the pressure passes read the planes outside the owned range straight from the neighbours' memory
+// (kernels_pressure_reg.cuh, PassRange): they consume no ghost depth and need no exchange, but leave the local ghost
+// planes of u,v,w stale.
+inline std::vector<Op> plan_step(const Geom& g, int iterations, int fuse, Carry& carry, bool peer_passes = false)
 {
     std::vector<Op> ops;
     const int D = g.D, G = g.ghost;
@@ -120,9 +123,14 @@ inline std::vector<Op> plan_step(const Geom& g, int iterations, int fuse, Carry&
         int K = 1;
         if (fuse >= 4 && total - done >= 4 && (done & 1) == 0) K = 4;
         else if (fuse >= 2 && total - done >= 2 && (done & 1) == 0) K = 2;
-        if (vel_d < K) exchange(SET_VEL_NOW);
-        ops.push_back({OP_PRESSURE, g.zlo, g.zhc + 1, done, K});
-        vel_d -= K;
+        if (peer_passes && g.world > 1 && K == 4) { // only the K = 4 register kernel reads peers
+            ops.push_back({OP_PRESSURE, g.own_node_lo(), g.own_node_hi() + 1, done, K});
+            vel_d = 0;
+        } else {
+            if (vel_d < K) exchange(SET_VEL_NOW);
+            ops.push_back({OP_PRESSURE, g.zlo, g.zhc + 1, done, K});
+            vel_d -= K;
+        }
         done += K;
     }
 

@@ -34,6 +34,27 @@ struct TimedSpan {
     cudaEvent_t e0, e1;
 };
 
+// byte offsets inside a slab's arena: [epoch counters][density x2][u x3][v x3][w x3] (x3 = ping, pong, scratch)
+struct ArenaLayout {
+    size_t counters = 0, smoke[2] = {0, 0}, u[3] = {0, 0, 0}, v[3] = {0, 0, 0}, w[3] = {0, 0, 0}, total = 0;
+};
+
+ArenaLayout make_layout(const slab::Geom& geom)
+{
+    const size_t P = (size_t)((geom.W + 1 + 7) / 8 * 8), SY = (size_t)geom.H + 1;
+    const size_t nzc = (size_t)(geom.zhc - geom.zlo), nzn = nzc + 1;
+    const size_t nb = (P * SY * nzn * sizeof(float) + 255) / 256 * 256;
+    const size_t cb = ((size_t)geom.W * geom.H * nzc * sizeof(float) + 255) / 256 * 256;
+    ArenaLayout l;
+    size_t o = 4096;
+    for (int i = 0; i < 2; i++) { l.smoke[i] = o; o += cb; }
+    for (int i = 0; i < 3; i++) { l.u[i] = o; o += nb; }
+    for (int i = 0; i < 3; i++) { l.v[i] = o; o += nb; }
+    for (int i = 0; i < 3; i++) { l.w[i] = o; o += nb; }
+    l.total = o;
+    return l;
+}
+
 } // namespace
 
 struct smk_sim {
@@ -66,8 +87,22 @@ struct smk_sim {
     slab::Carry carry{};
     smk_exchange_fn exchange = nullptr;
     void* exchange_ctx = nullptr;
-    int* d_flags = nullptr; // [0]: a backtrace left the valid planes of a slab (SMK_ERR_REACH)
+    int* d_flags = nullptr; // [0]: a backtrace left the valid planes of a slab (SMK_ERR_REACH); [1]: peer wait timed out
     long exchanges = 0;
+
+    // one allocation for every exchanged field so that a neighbour process can map it with ONE CUDA IPC handle
+    char* arena = nullptr;
+    ArenaLayout lay{};
+    int vel_id[2] = {0, 1}; // physical buffer (0..2) behind u/v/w[0], u/v/w[1] ...
+    int scratch_id = 2;     // ... and behind the scratch set; identical on every rank (same swap history)
+    struct Peer {
+        char* arena = nullptr;
+        bool ipc = false;
+        slab::Geom geom{};
+        ArenaLayout lay{};
+    } peer[2];              // [0] lower-z neighbour, [1] upper-z neighbour
+    bool p2p = false;       // all existing neighbours attached: native peer-memory halo path
+    unsigned epoch = 0;
 
     // host buffers registered for fast density readback
     std::vector<void*> registered;
@@ -242,31 +277,21 @@ int launch_halfsweep(smk_sim* s, int offset, int zlo_req = INT32_MIN, int zhi_re
 // ---- fused pressure passes (kernels_pressure_fused.cuh) ---------------------------------------------------
 // z-chunking shared by the fused kernels: enough CTAs to fill the SMs, as few lead-in/lead-out planes
 // (2K per chunk) as possible
-int pick_zchunk(const smk_sim* s, int tiles_xy, int K)
+int pick_zchunk(const smk_sim* s, int tiles_xy, int K, int nzn)
 {
-    const GridP& g = s->g;
     int best_n = 1;
     double best = -1.0;
-    for (int n = 1; n <= std::max(1, g.nzn / 4); n++) {
-        const int zc = (g.nzn + n - 1) / n;
-        const long ctas = (long)tiles_xy * ((g.nzn + zc - 1) / zc);
+    for (int n = 1; n <= std::max(1, nzn / 4); n++) {
+        const int zc = (nzn + n - 1) / n;
+        const long ctas = (long)tiles_xy * ((nzn + zc - 1) / zc);
         const long waves = (ctas + s->num_sms - 1) / s->num_sms;
         const double eff = (double)ctas / (double)(waves * s->num_sms) * (double)zc / (double)(zc + 2 * K);
         if (eff > best + 1e-9) { best = eff; best_n = n; }
     }
-    return (g.nzn + best_n - 1) / best_n;
+    return (nzn + best_n - 1) / best_n;
 }
 
-int ensure_scratch(smk_sim* s)
-{
-    if (s->scratch[0]) return SMK_OK;
-    const size_t nb = node_count(s->g) * sizeof(float);
-    for (int i = 0; i < 3; i++) {
-        CK(s, cudaMalloc(&s->scratch[i], nb));
-        CK(s, cudaMemsetAsync(s->scratch[i], 0, nb, s->stream));
-    }
-    return SMK_OK;
-}
+int ensure_scratch(smk_sim*) { return SMK_OK; } // the scratch set is part of the arena
 
 void swap_in_scratch(smk_sim* s)
 {
@@ -274,6 +299,7 @@ void swap_in_scratch(smk_sim* s)
     std::swap(s->u[n], s->scratch[0]);
     std::swap(s->v[n], s->scratch[1]);
     std::swap(s->w[n], s->scratch[2]);
+    std::swap(s->vel_id[n], s->scratch_id);
 }
 
 template <int K, int FUSED_NW, int FUSED_RPW>
@@ -290,7 +316,7 @@ int launch_fused_pass_cfg(smk_sim* s, int sweep0)
     int rc = ensure_scratch(s);
     if (rc) return rc;
     const int tx = (g.W + 1 + C::OX - 1) / C::OX, ty = (g.SY + C::OY - 1) / C::OY;
-    const int zchunk = pick_zchunk(s, tx * ty, K);
+    const int zchunk = pick_zchunk(s, tx * ty, K, g.nzn);
     const dim3 grid((unsigned)tx, (unsigned)ty, (unsigned)((g.nzn + zchunk - 1) / zchunk));
     const int n = s->now;
     kern<<<grid, C::THREADS, C::SMEM, s->stream>>>(g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2],
@@ -301,8 +327,43 @@ int launch_fused_pass_cfg(smk_sim* s, int sweep0)
 }
 
 // register-resident fused pass (kernels_pressure_reg.cuh): u, w in registers, v in shared memory
+// epoch handshake with the neighbours (peer-memory halo path): publish my epoch, wait for theirs
+int peer_sync(smk_sim* s)
+{
+    s->epoch++;
+    unsigned* theirs[2] = {nullptr, nullptr};
+    const unsigned* mine[2] = {nullptr, nullptr};
+    for (int side = 0; side < 2; side++) {
+        if (!s->peer[side].arena) continue;
+        // counter [k] of an arena is written by the neighbour on side k: I am my lower neighbour's upper neighbour
+        theirs[side] = reinterpret_cast<unsigned*>(s->peer[side].arena + s->peer[side].lay.counters) + (1 - side) * 32;
+        mine[side] = reinterpret_cast<const unsigned*>(s->arena + s->lay.counters) + side * 32;
+    }
+    smk::k_epoch_signal<<<1, 1, 0, s->stream>>>(theirs[0], theirs[1], s->epoch);
+    smk::k_epoch_wait<<<1, 1, 0, s->stream>>>(mine[0], mine[1], s->epoch, s->d_flags, (long long)2e10);
+    s->launches += 2;
+    CK(s, cudaGetLastError());
+    return SMK_OK;
+}
+
+smk::PeerPlanes peer_planes(const smk_sim* s, int side)
+{
+    smk::PeerPlanes p{nullptr, nullptr, nullptr, 0};
+    const auto& pe = s->peer[side];
+    if (!pe.arena) return p;
+    const int id = s->vel_id[s->now]; // same physical buffer on every rank (identical swap history)
+    p.u = reinterpret_cast<const float*>(pe.arena + pe.lay.u[id]);
+    p.v = reinterpret_cast<const float*>(pe.arena + pe.lay.v[id]);
+    p.w = reinterpret_cast<const float*>(pe.arena + pe.lay.w[id]);
+    p.zlo = pe.geom.zlo;
+    return p;
+}
+
+// register-resident fused pass (kernels_pressure_reg.cuh): u, w in registers, v in shared memory.
+// [out_lo, out_hi) = node planes to write; with peers attached the planes outside the owned range are read from the
+// neighbours' memory inside the kernel (after an epoch handshake), otherwise from the local ghost planes.
 template <int K, int NW>
-int launch_reg_pass(smk_sim* s, int sweep0)
+int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_peers)
 {
     using C = smk::RegCfg<K, NW>;
     const GridP& g = s->g;
@@ -312,25 +373,39 @@ int launch_reg_pass(smk_sim* s, int sweep0)
         CK(s, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         configured = true;
     }
-    int rc = ensure_scratch(s);
-    if (rc) return rc;
+    smk::PassRange pr{};
+    pr.out_lo = out_lo; pr.out_hi = out_hi;
+    pr.own_lo = g.zlo; pr.own_hi = g.zlo + g.nzn - 1; // default: everything stored counts as "own" (local source)
+    if (from_peers) {
+        int rc = peer_sync(s);
+        if (rc) return rc;
+        pr.own_lo = s->geom.own_node_lo(); pr.own_hi = s->geom.own_node_hi();
+        pr.lower = peer_planes(s, 0); pr.upper = peer_planes(s, 1);
+    }
+    const int nz = out_hi - out_lo;
     const int tx = (g.W + 1 + C::OX - 1) / C::OX, ty = (g.SY + C::OY - 1) / C::OY;
-    const int zchunk = pick_zchunk(s, tx * ty, K);
-    const dim3 grid((unsigned)tx, (unsigned)ty, (unsigned)((g.nzn + zchunk - 1) / zchunk));
+    const int zchunk = pick_zchunk(s, tx * ty, K, nz);
+    const dim3 grid((unsigned)tx, (unsigned)ty, (unsigned)((nz + zchunk - 1) / zchunk));
     const int n = s->now;
     kern<<<grid, C::THREADS, C::SMEM, s->stream>>>(g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2],
-                                                    s->code, sweep0, zchunk);
+                                                    s->code, sweep0, zchunk, pr);
     swap_in_scratch(s);
     count_launch(s, SMK_STAGE_PRESSURE);
     return SMK_OK;
 }
 
-template <int K>
-int launch_fused_pass(smk_sim* s, int sweep0)
+bool peer_passes(const smk_sim* s) // pressure passes may read the neighbours directly (K = 4 register kernel only)
 {
-    // tile shape (warps x rows per warp); tuning knob SMK_FUSED_CFG for experiments, default 24x2
     static const int cfg = getenv("SMK_FUSED_CFG") ? atoi(getenv("SMK_FUSED_CFG")) : 0;
-    if (K == 4 && cfg == 0) return launch_reg_pass<4, 16>(s, sweep0);
+    return s->p2p && s->geom.world > 1 && cfg == 0;
+}
+
+template <int K>
+int launch_fused_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_peers)
+{
+    // SMK_FUSED_CFG selects the older shared-memory kernel (warps x rows per warp) for experiments
+    static const int cfg = getenv("SMK_FUSED_CFG") ? atoi(getenv("SMK_FUSED_CFG")) : 0;
+    if (K == 4 && cfg == 0) return launch_reg_pass<4, 16>(s, sweep0, out_lo, out_hi, from_peers);
     switch (cfg) {
     case 163: return launch_fused_pass_cfg<K, 16, 3>(s, sweep0);
     case 124: return launch_fused_pass_cfg<K, 12, 4>(s, sweep0);
@@ -347,10 +422,12 @@ int effective_fuse(const smk_sim* s)
 }
 
 // half-sweeps [sweep0, sweep0 + K) on every stored plane (offsets alternate 0,1: cu:797-801)
-int run_pressure_pass(smk_sim* s, int sweep0, int K)
+int run_pressure_pass(smk_sim* s, int sweep0, int K, int out_lo = INT32_MIN, int out_hi = INT32_MAX, bool from_peers = false)
 {
-    if (K == 4) return launch_fused_pass<4>(s, sweep0);
-    if (K == 2) return launch_fused_pass<2>(s, sweep0);
+    out_lo = std::max(out_lo, s->g.zlo);
+    out_hi = std::min(out_hi, s->g.zlo + s->g.nzn);
+    if (K == 4) return launch_fused_pass<4>(s, sweep0, out_lo, out_hi, from_peers);
+    if (K == 2) return launch_fused_pass<2>(s, sweep0, out_lo, out_hi, false);
     return launch_halfsweep(s, sweep0 & 1);
 }
 
@@ -432,9 +509,45 @@ bool try_register(smk_sim* s, void* p, size_t bytes)
 }
 
 // halo exchange of one field set through the caller's transport (smk_set_exchange)
+// native halo exchange over peer-mapped memory: handshake, then PULL the neighbours' owned boundary planes into my
+// ghost planes (the neighbour's send region == my receive region, same global planes)
+int run_exchange_p2p(smk_sim* s, int set)
+{
+    const GridP& g = s->g;
+    int rc = peer_sync(s);
+    if (rc) return rc;
+    for (const slab::Region& r : slab::regions(s->geom, set)) {
+        const auto& pe = s->peer[r.side];
+        if (!pe.arena || r.recv_n <= 0) continue;
+        const size_t plane = set == slab::SET_VEL_NOW ? (size_t)g.nplane : (size_t)g.cplane;
+        const size_t n16 = (size_t)r.recv_n * plane * sizeof(float) / 16;
+        const int nf = set == slab::SET_VEL_NOW ? 3 : 1;
+        for (int i = 0; i < nf; i++) {
+            float* dst; const float* src;
+            if (set == slab::SET_VEL_NOW) {
+                float* mine[3] = {s->u[s->now], s->v[s->now], s->w[s->now]};
+                const int id = s->vel_id[s->now];
+                const size_t off[3] = {pe.lay.u[id], pe.lay.v[id], pe.lay.w[id]};
+                dst = mine[i] + (size_t)(r.recv_lo - g.zlo) * plane;
+                src = reinterpret_cast<const float*>(pe.arena + off[i]) + (size_t)(r.recv_lo - pe.geom.zlo) * plane;
+            } else {
+                dst = s->smoke[s->now] + (size_t)(r.recv_lo - g.zlo) * plane;
+                src = reinterpret_cast<const float*>(pe.arena + pe.lay.smoke[s->now]) + (size_t)(r.recv_lo - pe.geom.zlo) * plane;
+            }
+            const unsigned blocks = (unsigned)std::min<size_t>((n16 + 255) / 256, 4 * (size_t)s->num_sms);
+            smk::k_copy16<<<blocks, 256, 0, s->stream>>>(reinterpret_cast<float4*>(dst), reinterpret_cast<const float4*>(src), n16);
+            s->launches++;
+        }
+    }
+    s->exchanges++;
+    CK(s, cudaGetLastError());
+    return SMK_OK;
+}
+
 int run_exchange(smk_sim* s, int set)
 {
-    if (!s->exchange) return fail(s, SMK_ERR_TRANSPORT, "slab step needs a halo transport: call smk_set_exchange() first");
+    if (s->p2p) return run_exchange_p2p(s, set);
+    if (!s->exchange) return fail(s, SMK_ERR_TRANSPORT, "slab step needs a halo transport: call smk_set_exchange() or attach the peers");
     const GridP& g = s->g;
     std::vector<smk_halo_region> out;
     for (const slab::Region& r : slab::regions(s->geom, set)) {
@@ -463,7 +576,8 @@ int exec_op(smk_sim* s, const slab::Op& op, float dt)
     case slab::OP_FORCE: return stage_force_clamp(s, dt, op.a, op.b);
     case slab::OP_PRESSURE: {
         Span sp(s, SMK_STAGE_PRESSURE);
-        int rc = run_pressure_pass(s, op.p0, op.p1);
+        const bool from_peers = peer_passes(s) && op.p1 == 4;
+        int rc = from_peers ? run_pressure_pass(s, op.p0, op.p1, op.a, op.b, true) : run_pressure_pass(s, op.p0, op.p1);
         if (rc == SMK_OK) CK(s, cudaGetLastError());
         return rc;
     }
@@ -478,7 +592,8 @@ int exec_op(smk_sim* s, const slab::Op& op, float dt)
 int enqueue_step(smk_sim* s, float dt, float* density_host)
 {
     int rc = SMK_OK;
-    const std::vector<slab::Op> ops = slab::plan_step(s->geom, s->iterations, effective_fuse(s), s->carry);
+    const bool pp = peer_passes(s) && effective_fuse(s) == 4;
+    const std::vector<slab::Op> ops = slab::plan_step(s->geom, s->iterations, effective_fuse(s), s->carry, pp);
     for (size_t i = 0; i < ops.size() && rc == SMK_OK; i++) rc = exec_op(s, ops[i], dt);
     if (rc) return rc;
     if (density_host) { // this slab's OWNED planes of the new density (a single GPU owns everything)
@@ -589,17 +704,19 @@ int create_common(smk_sim** out, unsigned W, unsigned H, unsigned D, int rank, i
     } while (0)
 
     CKN(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    const size_t nb = node_count(g) * sizeof(float), cb = cell_count(g) * sizeof(float);
+    const size_t cb = cell_count(g) * sizeof(float);
+    s->lay = make_layout(geom);
+    CKN(cudaMalloc(&s->arena, s->lay.total));
+    CKN(cudaMemsetAsync(s->arena, 0, s->lay.total, s->stream)); // every buffer zero-initialised, counters 0
     for (int i = 0; i < 2; i++) {
-        CKN(cudaMalloc(&s->smoke[i], cb));
-        CKN(cudaMalloc(&s->u[i], nb));
-        CKN(cudaMalloc(&s->v[i], nb));
-        CKN(cudaMalloc(&s->w[i], nb));
-        CKN(cudaMemsetAsync(s->smoke[i], 0, cb, s->stream));
-        CKN(cudaMemsetAsync(s->u[i], 0, nb, s->stream));
-        CKN(cudaMemsetAsync(s->v[i], 0, nb, s->stream));
-        CKN(cudaMemsetAsync(s->w[i], 0, nb, s->stream));
+        s->smoke[i] = reinterpret_cast<float*>(s->arena + s->lay.smoke[i]);
+        s->u[i] = reinterpret_cast<float*>(s->arena + s->lay.u[i]);
+        s->v[i] = reinterpret_cast<float*>(s->arena + s->lay.v[i]);
+        s->w[i] = reinterpret_cast<float*>(s->arena + s->lay.w[i]);
     }
+    s->scratch[0] = reinterpret_cast<float*>(s->arena + s->lay.u[2]);
+    s->scratch[1] = reinterpret_cast<float*>(s->arena + s->lay.v[2]);
+    s->scratch[2] = reinterpret_cast<float*>(s->arena + s->lay.w[2]);
     const size_t mask_bytes = (size_t)g.cplane * g.nzm;
     CKN(cudaMalloc(&s->mask, mask_bytes));
     CKN(cudaMalloc(&s->d_flags, 64));
@@ -663,6 +780,21 @@ int smk_slab_plan(unsigned W, unsigned H, unsigned D, unsigned world, unsigned r
     return n;
 }
 
+int smk_slab_plan_p2p(unsigned W, unsigned H, unsigned D, unsigned world, unsigned rank, unsigned ghost, int iterations, int fuse,
+                      int steps, int* ops5, int max_ops)
+{
+    if (world < 1 || rank >= world || steps < 1) return -SMK_ERR_ARG;
+    const slab::Geom g = slab::make_geom((int)W, (int)H, (int)D, (int)world, (int)rank, (int)ghost);
+    slab::Carry carry = slab::initial_carry(g);
+    int n = 0;
+    for (int st = 0; st < steps; st++)
+        for (const slab::Op& op : slab::plan_step(g, iterations, fuse, carry, fuse == 4)) {
+            if (ops5 && n < max_ops) { int* o = ops5 + 5 * n; o[0] = op.kind; o[1] = op.a; o[2] = op.b; o[3] = op.p0; o[4] = op.p1; }
+            n++;
+        }
+    return n;
+}
+
 int smk_slab_regions(unsigned W, unsigned H, unsigned D, unsigned world, unsigned rank, unsigned ghost, int set, int* out5, int max_regions)
 {
     if (world < 1 || rank >= world) return -SMK_ERR_ARG;
@@ -682,10 +814,9 @@ int smk_destroy(smk_sim* s)
     for (void* p : s->registered) cudaHostUnregister(p);
     for (auto& sp : s->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
     for (auto e : s->free_events) cudaEventDestroy(e);
-    for (int i = 0; i < 2; i++) {
-        cudaFree(s->smoke[i]); cudaFree(s->u[i]); cudaFree(s->v[i]); cudaFree(s->w[i]);
-    }
-    for (int i = 0; i < 3; i++) cudaFree(s->scratch[i]);
+    for (int i = 0; i < 2; i++)
+        if (s->peer[i].arena && s->peer[i].ipc) cudaIpcCloseMemHandle(s->peer[i].arena);
+    cudaFree(s->arena);
     cudaFree(s->mask); cudaFree(s->code); cudaFree(s->d_scalar); cudaFree(s->d_flags);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     cudaGetLastError();
@@ -780,12 +911,12 @@ int smk_sync(smk_sim* s)
     if (!s) return SMK_ERR_ARG;
     CK(s, cudaStreamSynchronize(s->stream));
     if (s->geom.world > 1) { // slab runs: did a backtrace leave the valid planes?
-        int flag = 0;
-        CK(s, cudaMemcpy(&flag, s->d_flags, sizeof(int), cudaMemcpyDeviceToHost));
-        if (flag) {
-            cudaMemset(s->d_flags, 0, sizeof(int));
+        int flag[2] = {0, 0};
+        CK(s, cudaMemcpy(flag, s->d_flags, sizeof(flag), cudaMemcpyDeviceToHost));
+        if (flag[0] || flag[1]) cudaMemset(s->d_flags, 0, sizeof(flag));
+        if (flag[1]) return fail(s, SMK_ERR_TRANSPORT, "timed out waiting for a neighbour GPU (peer-memory halo path)");
+        if (flag[0])
             return fail(s, SMK_ERR_REACH, "a backtrace reached beyond the slab's valid ghost planes (|w|*dt >= 1 cell): increase ghost");
-        }
     }
     if (s->spans.size() > 4096) return fold_timers(s);
     return SMK_OK;
@@ -842,6 +973,64 @@ int smk_set_field(smk_sim* s, int field, int which, const void* host_src)
 }
 
 int smk_index_now(smk_sim* s) { return s ? s->now : -1; }
+
+// ---- peer-memory halo path (CUDA IPC between the per-GPU processes, or plain pointers inside one process) ----
+int smk_p2p_export(smk_sim* s, unsigned char* handle64)
+{
+    if (!s || !handle64) return SMK_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    cudaIpcMemHandle_t h;
+    CK(s, cudaIpcGetMemHandle(&h, s->arena));
+    memcpy(handle64, &h, 64);
+    return SMK_OK;
+}
+
+void* smk_p2p_arena(smk_sim* s) { return s ? s->arena : nullptr; }
+
+static int attach_common(smk_sim* s, int side, char* arena, bool ipc)
+{
+    auto& pe = s->peer[side];
+    pe.arena = arena; pe.ipc = ipc;
+    pe.geom = slab::make_geom(s->geom.W, s->geom.H, s->geom.D, s->geom.world, s->geom.rank + (side == 0 ? -1 : 1), s->geom.ghost);
+    pe.lay = make_layout(pe.geom);
+    s->p2p = (!s->geom.has_lower() || s->peer[0].arena) && (!s->geom.has_upper() || s->peer[1].arena);
+    return SMK_OK;
+}
+
+int smk_p2p_attach_ipc(smk_sim* s, int side, const unsigned char* handle64)
+{
+    if (!s || !handle64 || side < 0 || side > 1) return SMK_ERR_ARG;
+    if ((side == 0 && !s->geom.has_lower()) || (side == 1 && !s->geom.has_upper())) return fail(s, SMK_ERR_ARG, "no neighbour on that side");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    CK(s, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    return attach_common(s, side, static_cast<char*>(p), true);
+}
+
+int smk_p2p_attach_ptr(smk_sim* s, int side, void* peer_arena)
+{
+    if (!s || !peer_arena || side < 0 || side > 1) return SMK_ERR_ARG;
+    if ((side == 0 && !s->geom.has_lower()) || (side == 1 && !s->geom.has_upper())) return fail(s, SMK_ERR_ARG, "no neighbour on that side");
+    return attach_common(s, side, static_cast<char*>(peer_arena), false);
+}
+
+long smk_exchange_count(smk_sim* s) { return s ? s->exchanges : -1; }
+
+// Publish the NEXT epoch to the neighbours without waiting.  Only needed when several slabs are driven from one host
+// thread on one GPU (tests): there all signals of a synchronisation point must be enqueued before any wait, because
+// streams may share a hardware queue and a spinning wait would block a signal queued behind it.
+int smk_p2p_presignal(smk_sim* s)
+{
+    if (!s || !s->p2p) return SMK_ERR_ARG;
+    unsigned* theirs[2] = {nullptr, nullptr};
+    for (int side = 0; side < 2; side++)
+        if (s->peer[side].arena) theirs[side] = reinterpret_cast<unsigned*>(s->peer[side].arena + s->peer[side].lay.counters) + (1 - side) * 32;
+    smk::k_epoch_signal<<<1, 1, 0, s->stream>>>(theirs[0], theirs[1], s->epoch + 1);
+    s->launches++;
+    CK(s, cudaGetLastError());
+    return SMK_OK;
+}
 
 int smk_exec_op(smk_sim* s, const int* op5, float dt)
 {

@@ -40,6 +40,18 @@ def plan(W, H, D, world, rank, ghost, iterations=30, fuse=4, steps=1):
     return [(OP_NAMES[int(r[0])], int(r[1]), int(r[2]), int(r[3]), int(r[4])) for r in a]
 
 
+def plan_p2p(W, H, D, world, rank, ghost, iterations=30, fuse=4, steps=1):
+    """Like plan(), for the peer-memory path (pressure passes read the neighbours directly: no exchange for them)."""
+    L = binding.load_library()
+    n = L.smk_slab_plan_p2p(W, H, D, world, rank, ghost, iterations, fuse, steps, None, 0)
+    if n < 0:
+        raise binding.SmokeError(f"smk_slab_plan_p2p failed ({n})")
+    buf = (C.c_int * (5 * n))()
+    L.smk_slab_plan_p2p(W, H, D, world, rank, ghost, iterations, fuse, steps, buf, n)
+    a = np.frombuffer(buf, dtype=np.int32).reshape(n, 5)
+    return [(OP_NAMES[int(r[0])], int(r[1]), int(r[2]), int(r[3]), int(r[4])) for r in a]
+
+
 def regions(W, H, D, world, rank, ghost, set_id):
     """Halo regions of one exchange: [(side, send_lo, send_n, recv_lo, recv_n), ...] in global plane indices."""
     L = binding.load_library()
@@ -47,6 +59,28 @@ def regions(W, H, D, world, rank, ghost, set_id):
     n = L.smk_slab_regions(W, H, D, world, rank, ghost, set_id, buf, 2)
     a = np.frombuffer(buf, dtype=np.int32).reshape(2, 5)[:n]
     return [tuple(int(v) for v in r) for r in a]
+
+
+def attach_peers_ipc(sim, rank, world, dist, device):
+    """Multi-process setup of the peer-memory halo path: all-gather the 64-byte CUDA IPC handles of the slabs' arenas
+    (torch.distributed is only the plumbing) and map the two neighbours.  After this smk_step needs no transport."""
+    import torch
+    mine = torch.frombuffer(bytearray(sim.p2p_export()), dtype=torch.uint8).to(device)
+    allh = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    if rank > 0:
+        sim.p2p_attach_ipc(0, bytes(allh[rank - 1].cpu().numpy().tobytes()))
+    if rank < world - 1:
+        sim.p2p_attach_ipc(1, bytes(allh[rank + 1].cpu().numpy().tobytes()))
+
+
+def attach_peers_local(sims):
+    """Same for slabs that live in ONE process (virtual slabs on one GPU, tests): plain pointers."""
+    for r, s in enumerate(sims):
+        if r > 0:
+            s.p2p_attach_ptr(0, sims[r - 1].p2p_arena())
+        if r < len(sims) - 1:
+            s.p2p_attach_ptr(1, sims[r + 1].p2p_arena())
 
 
 class _DevBuf:
