@@ -117,13 +117,25 @@ int smk_set_solver(smk_sim* s, int variant, int iterations, int fuse);
  * the device->host round trip (the result stays on the device; smk_density_device()). */
 int smk_step(smk_sim* s, float dt, float* density_host);
 
-/* same, without waiting: returns after enqueueing; smk_sync() waits.  density_host may be NULL. */
+/* same, without waiting: returns after enqueueing; smk_sync() waits.  density_host may be NULL.  With a host buffer
+ * the readback is PIPELINED: the new density is snapshotted on the device and copied to the host on a second
+ * stream while the next step computes (the buffer holds step n's density once step n+1 has been enqueued and
+ * smk_sync() returned, or after the next smk_step_async has waited for it). */
 int smk_step_async(smk_sim* s, float dt, float* density_host);
 int smk_sync(smk_sim* s);
 
 /* device pointer to the density produced by the last step, reference layout (W*H*D floats).
  * Replaces the D2H + glTexSubImage3D round trip of cu:814 / boundingBox.cpp:380-385. */
 const float* smk_density_device(smk_sim* s);
+
+/* Copy the density of the last step into a 3-D CUDA array (cudaArray_t passed as void*; W x H x D, one float
+ * channel) on the step's stream -- e.g. the array of the renderer's GL_R32F texture mapped through CUDA-GL interop.
+ * Together with simulate(nullptr, dt) this removes the D2H + glTexSubImage3D round trip. */
+int smk_copy_density_to_array(smk_sim* s, void* cuda_array);
+/* test helpers: a plain 3-D float array standing in for the mapped texture */
+void* smk_test_array_create(unsigned W, unsigned H, unsigned D);
+int smk_test_array_read(void* cuda_array, float* host, unsigned W, unsigned H, unsigned D);
+void smk_test_array_destroy(void* cuda_array);
 
 /* run the whole step on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL = own stream */
 int smk_set_stream(smk_sim* s, void* cuda_stream);

@@ -80,6 +80,11 @@ def load_library():
     L.smk_density_device.argtypes = [_vp]
     L.smk_density_device.restype = _vp
     L.smk_set_stream.argtypes = [_vp, _vp]
+    L.smk_copy_density_to_array.argtypes = [_vp, _vp]
+    L.smk_test_array_create.argtypes = [C.c_uint] * 3
+    L.smk_test_array_create.restype = _vp
+    L.smk_test_array_read.argtypes = [_vp, _vp] + [C.c_uint] * 3
+    L.smk_test_array_destroy.argtypes = [_vp]
     L.smk_stage_flip.argtypes = [_vp]
     L.smk_stage_fill.argtypes = [_vp]
     L.smk_stage_force_clamp.argtypes = [_vp, _f]
@@ -199,6 +204,7 @@ class SmokeSim:
     def step_async(self, dt, host_ptr=None): self._ck(self.L.smk_step_async(self.h, dt, host_ptr))
     def sync(self): self._ck(self.L.smk_sync(self.h))
     def density_device(self): return self.L.smk_density_device(self.h)
+    def copy_density_to_array(self, cuda_array): self._ck(self.L.smk_copy_density_to_array(self.h, cuda_array))
 
     # -- stages
     def flip(self): self._ck(self.L.smk_stage_flip(self.h))

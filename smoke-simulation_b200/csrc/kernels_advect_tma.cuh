@@ -1,0 +1,201 @@
+// kernels_advect_tma.cuh -- u,v,w self-advection with TMA-staged tiles (sm_100a).
+//
+// Same arithmetic as k_advect_velocity (kernels_basic.cuh; reference velocityAdvectionU/V/W cu:527-615) -- it calls
+// the same rounding-exact helpers -- but the ~75 gathers of a node (three 8-point face sums + three trilinear
+// samples) are served from shared memory: a CTA owns a TX x TY tile of nodes and marches along z; every z-step the
+// TMA engine (cp.async.bulk.tensor.3d, one elected thread, completion on an mbarrier) drops the next (TX+2h) x (TY+2h)
+// plane of u, v and w -- tile plus backtrace halo (2 nodes; 4 in x for 16-byte alignment) -- into a ring of 2h+2 planes.  Out-of-range box parts (domain
+// edge, negative coordinates) are zero-filled by the TMA unit.  A backtrace that leaves the staged box (|vel|*dt >= 2
+// cells; the clamp bounds it near 3*sqrt(dt)) falls back to the global-memory sampler, so results do not
+// depend on the halo assumption.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "grid.h"
+#include "kernels_basic.cuh"
+
+namespace smk {
+
+struct AdvTma {
+    static constexpr int TX = 32, TY = 8, HALO = 2; // halo of 2 nodes in y and z
+    static constexpr int HX = 4;                    // x halo: the box must START on a 16-byte boundary (measured: a start
+                                                    // coordinate that is not a multiple of 4 floats raises "illegal instruction")
+    static constexpr int BX = TX + 2 * HX, BY = TY + 2 * HALO;     // 40 x 12 box (inner extent 160 B: multiple of 16)
+    static constexpr int NSLOT = 2 * HALO + 2;                     // planes z-2..z+2 in use + one in flight
+    static constexpr int PLANE = BX * BY;                          // floats per staged plane and field
+    static constexpr int SLOT_BYTES = (PLANE * 4 + 127) / 128 * 128; // TMA destinations are 128-byte aligned
+    static constexpr int SLOT_FLOATS = SLOT_BYTES / 4;
+    static constexpr int THREADS = TX * TY;
+    static constexpr size_t SMEM = (size_t)3 * NSLOT * SLOT_BYTES + NSLOT * 8 + 128;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: returns false after ~2^26 polls instead of hanging the GPU on a lost transaction
+__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    for (int it = 0; it < (1 << 26); it++) {
+        unsigned ok;
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+// staged planes of one field: tile-local coordinates, ring slot from the global plane index
+struct Staged {
+    const float* base; // [NSLOT][SLOT_FLOATS]
+    int x0, y0;        // global coordinates of box element (0,0)
+    int zc;            // plane being computed: planes zc-HALO .. zc+HALO are resident
+    __device__ __forceinline__ bool holds(int xa, int xb, int ya, int yb, int za, int zb) const
+    {
+        return xa >= x0 && xb < x0 + AdvTma::BX && ya >= y0 && yb < y0 + AdvTma::BY && za >= zc - AdvTma::HALO && zb <= zc + AdvTma::HALO;
+    }
+    __device__ __forceinline__ const float* row(int y, int z) const
+    {
+        const int slot = (z + 4 * AdvTma::NSLOT) % AdvTma::NSLOT;
+        return base + slot * AdvTma::SLOT_FLOATS + (y - y0) * AdvTma::BX - x0;
+    }
+    __device__ __forceinline__ float at(int x, int y, int z) const { return row(y, z)[x]; }
+};
+
+// clamped trilinear sample (sampleSmoke cu:451-484): same index / weight / summation code as sample_global, the
+// eight corners come from the staged planes when they are all resident
+__device__ __forceinline__ float sample_staged(const Staged& s, const float* __restrict__ f, long long sy, long long sz, int zlo,
+                                               float px, float py, float pz, float dx, float dy, float dz,
+                                               float bx, float by, float bz, int2 zv, int* __restrict__ flag)
+{
+    Tri t;
+    tri_axis(px, dx, bx, t.x0, t.x1, t.xw0, t.xw1);
+    tri_axis(py, dy, by, t.y0, t.y1, t.yw0, t.yw1);
+    tri_axis(pz, dz, bz, t.z0, t.z1, t.zw0, t.zw1);
+    if (s.holds(t.x0, t.x1, t.y0, t.y1, t.z0, t.z1) && t.z0 >= zv.x && t.z1 <= zv.y) {
+        const float* r00 = s.row(t.y0, t.z0); const float* r10 = s.row(t.y1, t.z0);
+        const float* r01 = s.row(t.y0, t.z1); const float* r11 = s.row(t.y1, t.z1);
+        return tri_combine(t, r00[t.x0], r00[t.x1], r10[t.x0], r10[t.x1], r01[t.x0], r01[t.x1], r11[t.x0], r11[t.x1]);
+    }
+    return sample_global(f, sy, sz, zlo, px, py, pz, dx, dy, dz, bx, by, bz, zv, flag); // long backtrace: global path
+}
+
+__global__ void __launch_bounds__(AdvTma::THREADS)
+k_advect_velocity_tma(GridP g, const __grid_constant__ CUtensorMap mu, const __grid_constant__ CUtensorMap mv,
+                      const __grid_constant__ CUtensorMap mw, const float* __restrict__ u0, const float* __restrict__ v0,
+                      const float* __restrict__ w0, float* __restrict__ u1, float* __restrict__ v1, float* __restrict__ w1,
+                      const unsigned char* __restrict__ code, float dt, int za, int zb, int zchunk, int2 zv,
+                      int* __restrict__ flag)
+{
+    using A = AdvTma;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* su = reinterpret_cast<float*>(smem_raw);
+    float* sv = su + A::NSLOT * A::SLOT_FLOATS;
+    float* sw = sv + A::NSLOT * A::SLOT_FLOATS;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sw + A::NSLOT * A::SLOT_FLOATS);
+
+    const int tid = threadIdx.x;
+    const int lx = tid % A::TX, ly = tid / A::TX;
+    const int tx0 = blockIdx.x * A::TX, ty0 = blockIdx.y * A::TY;      // first node of the tile
+    const int z_first = za + blockIdx.z * zchunk, z_last = min(z_first + zchunk, zb); // node planes [z_first, z_last)
+    if (z_first >= z_last) return;
+    const int x = tx0 + lx, y = ty0 + ly;
+    const int bx0 = tx0 - A::HX, by0 = ty0 - A::HALO;
+
+    if (tid == 0) {
+        for (int i = 0; i < A::NSLOT; i++) mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // plane p (global index) -> slot; tensor-map z coordinate is relative to the first stored plane
+    auto issue = [&](int p) {
+        const int slot = (p + 4 * A::NSLOT) % A::NSLOT;
+        mbar_expect_tx(&bars[slot], 3u * A::PLANE * 4u);
+        tma_load_3d(su + slot * A::SLOT_FLOATS, &mu, bx0, by0, p - g.zlo, &bars[slot]);
+        tma_load_3d(sv + slot * A::SLOT_FLOATS, &mv, bx0, by0, p - g.zlo, &bars[slot]);
+        tma_load_3d(sw + slot * A::SLOT_FLOATS, &mw, bx0, by0, p - g.zlo, &bars[slot]);
+    };
+    if (tid == 0)
+        for (int p = z_first - A::HALO; p <= z_first + A::HALO; p++) issue(p);
+
+    const float bx = (float)(unsigned)(g.W - 1), by = (float)(unsigned)(g.H - 1), bz = (float)(unsigned)(g.D - 1);
+    const long long P = g.P, S = g.nplane;
+    const bool xy_ok = x >= 1 && y >= 1 && x < g.W && y < g.H;
+
+    for (int z = z_first; z < z_last; z++) {
+        // every plane p is waited for exactly once, when it enters the window as z+HALO (the first step waits for all five)
+        for (int p = (z == z_first ? z - A::HALO : z + A::HALO); p <= z + A::HALO; p++) {
+            const int slot = (p + 4 * A::NSLOT) % A::NSLOT;
+            const unsigned use = (unsigned)((p - (z_first - A::HALO)) / A::NSLOT); // how often the slot was filled before
+            if (!mbar_wait(&bars[slot], use & 1u)) { flag[2] = 1; return; }
+        }
+        if (xy_ok && z >= 1 && z < g.D) {
+            const unsigned cd = code[code_index(g, x, y, z)];
+            const bool doU = (cd & CODE_SELF) && (cd & CODE_SX0) && y < g.H - 1 && z < g.D - 1;
+            const bool doV = (cd & CODE_SELF) && (cd & CODE_SY0) && x < g.W - 1 && z < g.D - 1;
+            const bool doW = (cd & CODE_SELF) && (cd & CODE_SZ0) && x < g.W - 1 && y < g.H - 1;
+            if (doU || doV || doW) {
+                const Staged U{su, bx0, by0, z}, V{sv, bx0, by0, z}, Wf{sw, bx0, by0, z};
+                const long long n = node_index(g, x, y, z);
+                // 8-point face sums in the reference's order (avgU/avgV/avgW cu:409-447), then *0.125
+                float au = 0.f, av = 0.f, aw = 0.f;
+                if (doV || doW) {
+                    float a = U.at(x, y, z - 1);
+                    a = __fadd_rn(a, U.at(x + 1, y, z - 1)); a = __fadd_rn(a, U.at(x, y - 1, z - 1)); a = __fadd_rn(a, U.at(x + 1, y - 1, z - 1));
+                    a = __fadd_rn(a, U.at(x, y, z)); a = __fadd_rn(a, U.at(x + 1, y, z)); a = __fadd_rn(a, U.at(x, y - 1, z));
+                    a = __fadd_rn(a, U.at(x + 1, y - 1, z));
+                    au = __fmul_rn(a, 0.125f);
+                }
+                if (doU || doW) {
+                    float a = V.at(x, y, z - 1);
+                    a = __fadd_rn(a, V.at(x - 1, y, z - 1)); a = __fadd_rn(a, V.at(x, y + 1, z - 1)); a = __fadd_rn(a, V.at(x - 1, y + 1, z - 1));
+                    a = __fadd_rn(a, V.at(x, y, z)); a = __fadd_rn(a, V.at(x - 1, y, z)); a = __fadd_rn(a, V.at(x, y + 1, z));
+                    a = __fadd_rn(a, V.at(x - 1, y + 1, z));
+                    av = __fmul_rn(a, 0.125f);
+                }
+                if (doU || doV) {
+                    float a = Wf.at(x, y, z);
+                    a = __fadd_rn(a, Wf.at(x - 1, y, z)); a = __fadd_rn(a, Wf.at(x, y - 1, z)); a = __fadd_rn(a, Wf.at(x - 1, y - 1, z));
+                    a = __fadd_rn(a, Wf.at(x, y, z - 1)); a = __fadd_rn(a, Wf.at(x - 1, y, z - 1)); a = __fadd_rn(a, Wf.at(x, y - 1, z - 1));
+                    a = __fadd_rn(a, Wf.at(x - 1, y - 1, z - 1));
+                    aw = __fmul_rn(a, 0.125f);
+                }
+                const float xh = half_up(x), yh = half_up(y), zh = half_up(z);
+                if (doU) {
+                    const float px = __fmaf_rn(-U.at(x, y, z), dt, (float)x);
+                    const float py = __fmaf_rn(-av, dt, yh);
+                    const float pz = __fmaf_rn(-aw, dt, zh);
+                    u1[n] = sample_staged(U, u0, P, S, g.zlo, px, py, pz, 0.f, .5f, .5f, bx, by, bz, zv, flag);
+                }
+                if (doV) {
+                    const float px = __fmaf_rn(-au, dt, xh);
+                    const float py = __fmaf_rn(-V.at(x, y, z), dt, (float)y);
+                    const float pz = __fmaf_rn(-aw, dt, zh);
+                    v1[n] = sample_staged(V, v0, P, S, g.zlo, px, py, pz, .5f, 0.f, .5f, bx, by, bz, zv, flag);
+                }
+                if (doW) {
+                    const float px = __fmaf_rn(-au, dt, xh);
+                    const float py = __fmaf_rn(-av, dt, yh);
+                    const float pz = __fmaf_rn(-Wf.at(x, y, z), dt, (float)z);
+                    w1[n] = sample_staged(Wf, w0, P, S, g.zlo, px, py, pz, .5f, .5f, 0.f, bx, by, bz, zv, flag);
+                }
+            }
+        }
+        __syncthreads(); // plane z-HALO is no longer read: its slot may take plane z+HALO+1
+        if (tid == 0 && z + 1 < z_last) issue(z + A::HALO + 1);
+    }
+}
+
+} // namespace smk

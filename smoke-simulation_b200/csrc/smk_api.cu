@@ -4,6 +4,7 @@
 // cu:124-248, drawObjects cu:714-771, simulate cu:774-819) with an explicit handle, one CUDA stream, kernel
 // parameters instead of per-step H2D copies of the object arrays, and events for per-stage timing.
 // There is no CPU fallback anywhere in this file: if CUDA is unavailable every call fails with SMK_ERR_CUDA.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -20,6 +21,7 @@
 #include "kernels_basic.cuh"
 #include "kernels_pressure_fused.cuh"
 #include "kernels_pressure_reg.cuh"
+#include "kernels_advect_tma.cuh"
 #include "slab_plan.h"
 
 namespace {
@@ -104,8 +106,18 @@ struct smk_sim {
     bool p2p = false;       // all existing neighbours attached: native peer-memory halo path
     unsigned epoch = 0;
 
+    // TMA descriptors of the three physical buffers of u, v, w (box = advection tile + halo), [field][physical id]
+    CUtensorMap tmap[3][3];
+    bool tma_ok = false;
+
     // host buffers registered for fast density readback
     std::vector<void*> registered;
+    // pipelined readback (smk_step_async with a host buffer): the new density is snapshotted device-to-device and
+    // copied to the host on a second stream while the next step computes
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_snap = nullptr, ev_copied = nullptr;
+    float* snapshot = nullptr;
+    bool copy_pending = false;
 
     // timing
     std::vector<TimedSpan> spans;
@@ -330,6 +342,8 @@ int launch_fused_pass_cfg(smk_sim* s, int sweep0)
 // epoch handshake with the neighbours (peer-memory halo path): publish my epoch, wait for theirs
 int peer_sync(smk_sim* s)
 {
+    static const bool nosync = getenv("SMK_DBG_NOSYNC") != nullptr; // timing experiments only (races!)
+    if (nosync) return SMK_OK;
     s->epoch++;
     unsigned* theirs[2] = {nullptr, nullptr};
     const unsigned* mine[2] = {nullptr, nullptr};
@@ -457,10 +471,29 @@ int stage_advect_velocity(smk_sim* s, float dt, int za, int zb, int vlo, int vhi
     za = std::max(za, std::max(1, g.zlo));
     zb = std::min(zb, std::min(g.D, g.zlo + g.nzc));
     if (zb > za) {
-        static const int by = getenv("SMK_ADV_BY") ? atoi(getenv("SMK_ADV_BY")) : 4, bz = getenv("SMK_ADV_BZ") ? atoi(getenv("SMK_ADV_BZ")) : 2;
-        const dim3 blk(32, by, bz), grd((g.W + 31) / 32, (g.H + by - 1) / by, (zb - za + bz - 1) / bz);
-        smk::k_advect_velocity<<<grd, blk, 0, s->stream>>>(
-            g, s->u[n], s->v[n], s->w[n], s->u[p], s->v[p], s->w[p], s->code, dt, za, zb, make_int2(vlo, vhi), s->d_flags);
+        static const int use_tma = getenv("SMK_ADVECT_TMA") ? atoi(getenv("SMK_ADVECT_TMA")) : 1;
+        if (use_tma && s->tma_ok) {
+            // TMA-staged tiles (kernels_advect_tma.cuh): tile + halo planes land in shared memory, gathers are LDS
+            using A = smk::AdvTma;
+            static bool configured = false;
+            if (!configured) {
+                CK(s, cudaFuncSetAttribute(smk::k_advect_velocity_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A::SMEM));
+                configured = true;
+            }
+            const int id = s->vel_id[n];
+            const int tiles = ((g.W + A::TX - 1) / A::TX) * ((g.H + A::TY - 1) / A::TY);
+            int zchunk = zb - za; // enough CTAs for ~8 per SM, chunks of at least 16 planes (5 lead-in planes each)
+            while (zchunk > 16 && (long)tiles * ((zb - za + zchunk - 1) / zchunk) < 8L * s->num_sms) zchunk = (zchunk + 1) / 2;
+            const dim3 grd((g.W + A::TX - 1) / A::TX, (g.H + A::TY - 1) / A::TY, (zb - za + zchunk - 1) / zchunk);
+            smk::k_advect_velocity_tma<<<grd, A::THREADS, A::SMEM, s->stream>>>(
+                g, s->tmap[0][id], s->tmap[1][id], s->tmap[2][id], s->u[n], s->v[n], s->w[n], s->u[p], s->v[p], s->w[p], s->code, dt,
+                za, zb, zchunk, make_int2(vlo, vhi), s->d_flags);
+        } else {
+            static const int by = getenv("SMK_ADV_BY") ? atoi(getenv("SMK_ADV_BY")) : 4, bz = getenv("SMK_ADV_BZ") ? atoi(getenv("SMK_ADV_BZ")) : 2;
+            const dim3 blk(32, by, bz), grd((g.W + 31) / 32, (g.H + by - 1) / by, (zb - za + bz - 1) / bz);
+            smk::k_advect_velocity<<<grd, blk, 0, s->stream>>>(
+                g, s->u[n], s->v[n], s->w[n], s->u[p], s->v[p], s->w[p], s->code, dt, za, zb, make_int2(vlo, vhi), s->d_flags);
+        }
         count_launch(s, SMK_STAGE_ADVECT_VEL);
     }
     CK(s, cudaGetLastError());
@@ -589,7 +622,7 @@ int exec_op(smk_sim* s, const slab::Op& op, float dt)
 }
 
 // one step = the plan of slab_plan.h executed with CUDA kernels (a single GPU is the 1-slab case: no exchanges)
-int enqueue_step(smk_sim* s, float dt, float* density_host)
+int enqueue_step(smk_sim* s, float dt, float* density_host, bool pipelined = false)
 {
     int rc = SMK_OK;
     const bool pp = peer_passes(s) && effective_fuse(s) == 4;
@@ -602,8 +635,26 @@ int enqueue_step(smk_sim* s, float dt, float* density_host)
         const size_t bytes = (size_t)(s->geom.c1 - s->geom.c0) * g.cplane * sizeof(float);
         float* dst = density_host + (size_t)s->geom.c0 * g.cplane;
         try_register(s, dst, bytes);
-        CK(s, cudaMemcpyAsync(dst, s->smoke[s->past] + (size_t)(s->geom.c0 - g.zlo) * g.cplane, bytes, cudaMemcpyDeviceToHost,
-                              s->stream));
+        const float* src = s->smoke[s->past] + (size_t)(s->geom.c0 - g.zlo) * g.cplane;
+        if (!pipelined) {
+            CK(s, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s->stream));
+        } else {
+            // the next step's source fill writes into this buffer: snapshot it (device to device, ~45 us at 256^3), then
+            // let the copy engine move the snapshot to the host while the next step runs
+            if (!s->copy_stream) {
+                CK(s, cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+                CK(s, cudaEventCreateWithFlags(&s->ev_snap, cudaEventDisableTiming));
+                CK(s, cudaEventCreateWithFlags(&s->ev_copied, cudaEventDisableTiming));
+                CK(s, cudaMalloc(&s->snapshot, bytes));
+            }
+            if (s->copy_pending) CK(s, cudaStreamWaitEvent(s->stream, s->ev_copied, 0)); // previous snapshot fully on the host
+            CK(s, cudaMemcpyAsync(s->snapshot, src, bytes, cudaMemcpyDeviceToDevice, s->stream));
+            CK(s, cudaEventRecord(s->ev_snap, s->stream));
+            CK(s, cudaStreamWaitEvent(s->copy_stream, s->ev_snap, 0));
+            CK(s, cudaMemcpyAsync(dst, s->snapshot, bytes, cudaMemcpyDeviceToHost, s->copy_stream));
+            CK(s, cudaEventRecord(s->ev_copied, s->copy_stream));
+            s->copy_pending = true;
+        }
     }
     return SMK_OK;
 }
@@ -656,6 +707,36 @@ int copy_field(smk_sim* s, const FieldRef& f, void* host, bool to_host)
     CK(s, cudaMemcpy3DAsync(&p, s->stream));
     CK(s, cudaStreamSynchronize(s->stream));
     return SMK_OK;
+}
+
+// cuTensorMapEncodeTiled is a driver-API entry point: fetched through the runtime so that the library does not link libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+bool build_tensor_maps(smk_sim* s)
+{
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    const GridP& g = s->g;
+    const cuuint64_t dims[3] = {(cuuint64_t)g.P, (cuuint64_t)g.SY, (cuuint64_t)g.nzn};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.P * 4, (cuuint64_t)g.nplane * 4}; // bytes, dims 1 and 2
+    const cuuint32_t box[3] = {smk::AdvTma::BX, smk::AdvTma::BY, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    for (int f = 0; f < 3; f++)
+        for (int id = 0; id < 3; id++) {
+            const size_t off = f == 0 ? s->lay.u[id] : f == 1 ? s->lay.v[id] : s->lay.w[id];
+            CUresult r = ((EncodeTiledFn)fn)(&s->tmap[f][id], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s->arena + off, dims, strides, box, estr,
+                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return false;
+        }
+    return true;
 }
 
 int create_common(smk_sim** out, unsigned W, unsigned H, unsigned D, int rank, int world, int ghost, const float* smoke0_full)
@@ -730,6 +811,7 @@ int create_common(smk_sim** out, unsigned W, unsigned H, unsigned D, int rank, i
     if (smoke0_full)
         CKN(cudaMemcpyAsync(s->smoke[0], smoke0_full + (size_t)g.zlo * g.cplane, cb, cudaMemcpyHostToDevice, s->stream));
     CKN(cudaStreamSynchronize(s->stream));
+    s->tma_ok = build_tensor_maps(s);
 #undef CKN
     *out = s;
     return SMK_OK;
@@ -811,6 +893,10 @@ int smk_destroy(smk_sim* s)
 {
     if (!s) return SMK_ERR_ARG;
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
+    if (s->ev_snap) cudaEventDestroy(s->ev_snap);
+    if (s->ev_copied) cudaEventDestroy(s->ev_copied);
+    cudaFree(s->snapshot);
     for (void* p : s->registered) cudaHostUnregister(p);
     for (auto& sp : s->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
     for (auto e : s->free_events) cudaEventDestroy(e);
@@ -903,17 +989,19 @@ int smk_set_stream(smk_sim* s, void* cuda_stream)
 int smk_step_async(smk_sim* s, float dt, float* density_host)
 {
     if (!s) return SMK_ERR_ARG;
-    return enqueue_step(s, dt, density_host);
+    return enqueue_step(s, dt, density_host, true);
 }
 
 int smk_sync(smk_sim* s)
 {
     if (!s) return SMK_ERR_ARG;
     CK(s, cudaStreamSynchronize(s->stream));
+    if (s->copy_pending) { CK(s, cudaStreamSynchronize(s->copy_stream)); s->copy_pending = false; }
     if (s->geom.world > 1) { // slab runs: did a backtrace leave the valid planes?
-        int flag[2] = {0, 0};
+        int flag[3] = {0, 0, 0};
         CK(s, cudaMemcpy(flag, s->d_flags, sizeof(flag), cudaMemcpyDeviceToHost));
-        if (flag[0] || flag[1]) cudaMemset(s->d_flags, 0, sizeof(flag));
+        if (flag[0] || flag[1] || flag[2]) cudaMemset(s->d_flags, 0, sizeof(flag));
+        if (flag[2]) return fail(s, SMK_ERR_CUDA, "a TMA transaction of the advection kernel did not complete");
         if (flag[1]) return fail(s, SMK_ERR_TRANSPORT, "timed out waiting for a neighbour GPU (peer-memory halo path)");
         if (flag[0])
             return fail(s, SMK_ERR_REACH, "a backtrace reached beyond the slab's valid ghost planes (|w|*dt >= 1 cell): increase ghost");
@@ -931,6 +1019,42 @@ int smk_step(smk_sim* s, float dt, float* density_host)
 }
 
 const float* smk_density_device(smk_sim* s) { return s ? s->smoke[s->past] : nullptr; }
+
+// the renderer samples the density as an R32F 3-D texture (boundingBox.cpp:364-385).  With CUDA-GL interop
+// (cudaGraphicsGLRegisterImage on m_gridTex -> cudaGraphicsSubResourceGetMappedArray) the new density goes straight
+// into that array: one device-to-device 3-D copy on the step's stream, no host round trip.
+int smk_copy_density_to_array(smk_sim* s, void* cuda_array)
+{
+    if (!s || !cuda_array) return SMK_ERR_ARG;
+    const GridP& g = s->g;
+    cudaMemcpy3DParms p{};
+    p.srcPtr = make_cudaPitchedPtr(s->smoke[s->past] + (size_t)(s->geom.c0 - g.zlo) * g.cplane, (size_t)g.W * 4, (size_t)g.W, (size_t)g.H);
+    p.dstArray = static_cast<cudaArray_t>(cuda_array);
+    p.dstPos = make_cudaPos(0, 0, (size_t)s->geom.c0);
+    p.extent = make_cudaExtent((size_t)g.W, (size_t)g.H, (size_t)(s->geom.c1 - s->geom.c0));
+    p.kind = cudaMemcpyDeviceToDevice;
+    CK(s, cudaMemcpy3DAsync(&p, s->stream));
+    return SMK_OK;
+}
+
+// test helpers for the above (a plain 3-D float array stands in for the mapped GL texture)
+void* smk_test_array_create(unsigned W, unsigned H, unsigned D)
+{
+    cudaArray_t a = nullptr;
+    cudaChannelFormatDesc d = cudaCreateChannelDesc<float>();
+    if (cudaMalloc3DArray(&a, &d, make_cudaExtent(W, H, D)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a;
+}
+int smk_test_array_read(void* cuda_array, float* host, unsigned W, unsigned H, unsigned D)
+{
+    cudaMemcpy3DParms p{};
+    p.srcArray = static_cast<cudaArray_t>(cuda_array);
+    p.dstPtr = make_cudaPitchedPtr(host, (size_t)W * 4, W, H);
+    p.extent = make_cudaExtent(W, H, D);
+    p.kind = cudaMemcpyDeviceToHost;
+    return cudaMemcpy3D(&p) == cudaSuccess ? SMK_OK : SMK_ERR_CUDA;
+}
+void smk_test_array_destroy(void* cuda_array) { cudaFreeArray(static_cast<cudaArray_t>(cuda_array)); }
 
 int smk_stage_flip(smk_sim* s) { if (!s) return SMK_ERR_ARG; flip(s); return SMK_OK; }
 int smk_stage_fill(smk_sim* s) { return s ? stage_fill(s) : SMK_ERR_ARG; }

@@ -235,3 +235,39 @@ def test_fused_full_steps_c1_obstacle(po, smk):
         a.step(po.tick_dt(t)); b.step(po.tick_dt(t))
     compare(po, a, b, "C1 fused x4")
     a.close()
+
+
+def test_pipelined_readback_delivers_every_step(po, smk):
+    """smk_step_async with a host buffer: snapshot + copy on a second stream; after smk_sync the buffer holds the
+    density of the last enqueued step, and intermediate steps were delivered in order."""
+    import ctypes
+    sc = po.scaled_scene("C1", 40)
+    a, b = make_pair(po, smk, sc)
+    host = np.zeros((40, 40, 40), dtype=np.float32)
+    for t in range(5):
+        a.step_async(po.tick_dt(t), host.ctypes.data_as(ctypes.c_void_p)); b.step(po.tick_dt(t))
+        if t == 2:
+            a.sync()
+            assert np.array_equal(host, b.get_field(po.SMOKE, po.PAST))
+    a.sync()
+    assert np.array_equal(host, b.get_field(po.SMOKE, po.PAST))
+    assert np.array_equal(host, a.get_field(po.SMOKE, po.PAST))
+    a.close()
+
+
+def test_density_to_cuda_array_without_host_round_trip(po, smk):
+    """simulate(nullptr, dt) + device-to-array copy == what the reference uploads with glTexSubImage3D."""
+    sc = po.scaled_scene("C1", 32)
+    a, b = make_pair(po, smk, sc)
+    L = smk.load_library()
+    arr = L.smk_test_array_create(32, 32, 32)
+    assert arr
+    for t in range(4):
+        a.step(po.tick_dt(t), None); b.step(po.tick_dt(t))
+        a.copy_density_to_array(arr)
+    a.sync()
+    out = np.zeros((32, 32, 32), dtype=np.float32)
+    assert L.smk_test_array_read(arr, out.ctypes.data_as(__import__("ctypes").c_void_p), 32, 32, 32) == 0
+    assert np.array_equal(out, b.get_field(po.SMOKE, po.PAST))
+    L.smk_test_array_destroy(arr)
+    a.close()
