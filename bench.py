@@ -249,11 +249,23 @@ def main():
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     transport = None
+    transport_name = None
     if world > 1:
         sim = smk.SmokeSim(W, H, D, slab=(rank, world), ghost=args.ghost)
+        transport_name = args.transport
         if args.transport == "p2p":     # peer-mapped memory over NVLink (CUDA IPC): no Python, no NCCL in the step
-            smk.slab.attach_peers_ipc(sim, rank, world, dist, torch.device("cuda", local_rank))
-        else:                           # torch.distributed send/recv (NCCL) through the transport callback
+            ok = 1
+            try:
+                smk.slab.attach_peers_ipc(sim, rank, world, dist, torch.device("cuda", local_rank))
+            except Exception as ex:   # e.g. no peer access between two GPUs: every rank falls back together
+                print(f"[bench rank {rank}] peer-memory attach failed ({ex}); falling back to NCCL", file=sys.stderr)
+                ok = 0
+            tok = torch.tensor([ok], device="cuda"); dist.all_reduce(tok, op=dist.ReduceOp.MIN)
+            if int(tok.item()) == 0:
+                sim.close()
+                sim = smk.SmokeSim(W, H, D, slab=(rank, world), ghost=args.ghost)
+                transport_name = "nccl"
+        if transport_name == "nccl":    # torch.distributed send/recv (NCCL) through the transport callback
             transport = smk.slab.TorchTransport(rank, world)
             sim.set_exchange(transport)
     else:
@@ -317,6 +329,8 @@ def main():
 
 
     # ---- extra: the same with the pipelined readback of smk_step_async (snapshot + copy on a second stream) --
+    sim.step_async(po.tick_dt(tick), host_ptr); tick += 1   # creates the copy stream / snapshot buffer
+    sim.sync()
     barrier()
     w0 = time.perf_counter()
     for _ in range(K):
@@ -358,7 +372,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": label + "; reference schedule RBGS omega=1.9 x30", "grid": [W, H, D], "solver": "rbgs",
                        "iterations": 30, "fuse": args.fuse, "parallelism": f"zslab{world}", "ghost": args.ghost if world > 1 else 0,
-                       "transport": (args.transport if world > 1 else None),
+                       "transport": transport_name,
                        "halo_exchanges_per_step": exchanges / K,
                        "l2": f"state per GPU {(2 * cells_local * 4 + 9 * (W + 1) * (H + 1) * (c1 - c0 + 1) * 4 + 2 * cells_local) / 1e6:.0f} MB "
                              "(> 126 MB L2): inputs larger than L2, no explicit flush"},

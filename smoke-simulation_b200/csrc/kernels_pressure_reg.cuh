@@ -139,6 +139,7 @@ struct PeerPlanes {
 struct PassRange {
     int out_lo, out_hi;  // node planes this launch writes: [out_lo, out_hi)
     int own_lo, own_hi;  // node planes owned by this slab (inclusive); outside them a peer is the source if present
+    int chunk_first, chunk_step; // z-chunk of block z = chunk_first + blockIdx.z * chunk_step (boundary / interior launches)
     PeerPlanes lower, upper;
 };
 
@@ -159,7 +160,7 @@ k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ 
     const int yl = wid + (lane >> 4) * NW;                   // this half-warp's row
     const int x0 = blockIdx.x * C::OX - K;
     const int y0 = blockIdx.y * C::OY - K;
-    const int zo0 = pr.out_lo + blockIdx.z * zchunk;         // output node planes [zo0, zo1)
+    const int zo0 = pr.out_lo + (pr.chunk_first + (int)blockIdx.z * pr.chunk_step) * zchunk; // output node planes [zo0, zo1)
     const int zo1 = min(zo0 + zchunk, pr.out_hi);
     const int t0 = zo0 - K, t1 = zo1 + K - 1;                // planes that enter the ring
     const int xg = x0 + 4 * h, yg = y0 + yl;

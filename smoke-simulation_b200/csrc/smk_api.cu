@@ -105,6 +105,8 @@ struct smk_sim {
     } peer[2];              // [0] lower-z neighbour, [1] upper-z neighbour
     bool p2p = false;       // all existing neighbours attached: native peer-memory halo path
     unsigned epoch = 0;
+    cudaStream_t aux_stream = nullptr; // boundary z-chunks of a peer-reading pass run here, behind the epoch wait,
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr; // while the interior chunks already run on the main stream
 
     // TMA descriptors of the three physical buffers of u, v, w (box = advection tile + halo), [field][physical id]
     CUtensorMap tmap[3][3];
@@ -340,24 +342,47 @@ int launch_fused_pass_cfg(smk_sim* s, int sweep0)
 
 // register-resident fused pass (kernels_pressure_reg.cuh): u, w in registers, v in shared memory
 // epoch handshake with the neighbours (peer-memory halo path): publish my epoch, wait for theirs
-int peer_sync(smk_sim* s)
+void peer_counters(smk_sim* s, unsigned* theirs[2], const unsigned* mine[2])
 {
-    static const bool nosync = getenv("SMK_DBG_NOSYNC") != nullptr; // timing experiments only (races!)
-    if (nosync) return SMK_OK;
-    s->epoch++;
-    unsigned* theirs[2] = {nullptr, nullptr};
-    const unsigned* mine[2] = {nullptr, nullptr};
+    theirs[0] = theirs[1] = nullptr;
+    mine[0] = mine[1] = nullptr;
     for (int side = 0; side < 2; side++) {
         if (!s->peer[side].arena) continue;
         // counter [k] of an arena is written by the neighbour on side k: I am my lower neighbour's upper neighbour
         theirs[side] = reinterpret_cast<unsigned*>(s->peer[side].arena + s->peer[side].lay.counters) + (1 - side) * 32;
         mine[side] = reinterpret_cast<const unsigned*>(s->arena + s->lay.counters) + side * 32;
     }
-    smk::k_epoch_signal<<<1, 1, 0, s->stream>>>(theirs[0], theirs[1], s->epoch);
-    smk::k_epoch_wait<<<1, 1, 0, s->stream>>>(mine[0], mine[1], s->epoch, s->d_flags, (long long)2e10);
-    s->launches += 2;
+}
+
+int peer_signal(smk_sim* s, cudaStream_t st) // publish the next epoch: everything enqueued before is final
+{
+    unsigned* theirs[2]; const unsigned* mine[2];
+    peer_counters(s, theirs, mine);
+    s->epoch++;
+    smk::k_epoch_signal<<<1, 1, 0, st>>>(theirs[0], theirs[1], s->epoch);
+    s->launches++;
     CK(s, cudaGetLastError());
     return SMK_OK;
+}
+
+int peer_wait(smk_sim* s, cudaStream_t st) // wait until both neighbours published the current epoch
+{
+    unsigned* theirs[2]; const unsigned* mine[2];
+    peer_counters(s, theirs, mine);
+    smk::k_epoch_wait<<<1, 1, 0, st>>>(mine[0], mine[1], s->epoch, s->d_flags, (long long)2e10);
+    s->launches++;
+    CK(s, cudaGetLastError());
+    return SMK_OK;
+}
+
+// epoch handshake with the neighbours (peer-memory halo path): publish my epoch, wait for theirs
+int peer_sync(smk_sim* s)
+{
+    static const bool nosync = getenv("SMK_DBG_NOSYNC") != nullptr; // timing experiments only (races!)
+    if (nosync) return SMK_OK;
+    int rc = peer_signal(s, s->stream);
+    if (rc) return rc;
+    return peer_wait(s, s->stream);
 }
 
 smk::PeerPlanes peer_planes(const smk_sim* s, int side)
@@ -390,19 +415,51 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
     smk::PassRange pr{};
     pr.out_lo = out_lo; pr.out_hi = out_hi;
     pr.own_lo = g.zlo; pr.own_hi = g.zlo + g.nzn - 1; // default: everything stored counts as "own" (local source)
-    if (from_peers) {
-        int rc = peer_sync(s);
-        if (rc) return rc;
-        pr.own_lo = s->geom.own_node_lo(); pr.own_hi = s->geom.own_node_hi();
-        pr.lower = peer_planes(s, 0); pr.upper = peer_planes(s, 1);
-    }
+    pr.chunk_first = 0; pr.chunk_step = 1;
     const int nz = out_hi - out_lo;
     const int tx = (g.W + 1 + C::OX - 1) / C::OX, ty = (g.SY + C::OY - 1) / C::OY;
     const int zchunk = pick_zchunk(s, tx * ty, K, nz);
-    const dim3 grid((unsigned)tx, (unsigned)ty, (unsigned)((nz + zchunk - 1) / zchunk));
+    const int nchunks = (nz + zchunk - 1) / zchunk;
     const int n = s->now;
-    kern<<<grid, C::THREADS, C::SMEM, s->stream>>>(g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2],
-                                                    s->code, sweep0, zchunk, pr);
+    static const bool overlap = getenv("SMK_P2P_NO_OVERLAP") == nullptr;
+    if (from_peers) {
+        pr.own_lo = s->geom.own_node_lo(); pr.own_hi = s->geom.own_node_hi();
+        pr.lower = peer_planes(s, 0); pr.upper = peer_planes(s, 1);
+    }
+    if (from_peers && overlap && nchunks >= 3 && zchunk >= K) {
+        // The first and last z-chunk read neighbour planes; the interior chunks do not and never write planes a
+        // neighbour may still be reading.  So: publish my epoch, start the interior chunks at once on the main stream, and
+        // run the two boundary chunks on a second stream behind the epoch wait -- the handshake latency and the skew
+        // between the GPUs hide behind the interior work.
+        if (!s->aux_stream) {
+            CK(s, cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
+            CK(s, cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+            CK(s, cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+        }
+        int rc = peer_signal(s, s->stream);
+        if (rc) return rc;
+        CK(s, cudaEventRecord(s->ev_fork, s->stream));
+        CK(s, cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0));
+        if ((rc = peer_wait(s, s->aux_stream))) return rc;
+        smk::PassRange pb = pr;
+        pb.chunk_first = 0; pb.chunk_step = nchunks - 1;
+        kern<<<dim3((unsigned)tx, (unsigned)ty, 2u), C::THREADS, C::SMEM, s->aux_stream>>>(
+            g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk, pb);
+        CK(s, cudaEventRecord(s->ev_join, s->aux_stream));
+        smk::PassRange pi = pr;
+        pi.chunk_first = 1; pi.chunk_step = 1;
+        kern<<<dim3((unsigned)tx, (unsigned)ty, (unsigned)(nchunks - 2)), C::THREADS, C::SMEM, s->stream>>>(
+            g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk, pi);
+        CK(s, cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+        s->launches++;
+    } else {
+        if (from_peers) {
+            int rc = peer_sync(s);
+            if (rc) return rc;
+        }
+        kern<<<dim3((unsigned)tx, (unsigned)ty, (unsigned)nchunks), C::THREADS, C::SMEM, s->stream>>>(
+            g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk, pr);
+    }
     swap_in_scratch(s);
     count_launch(s, SMK_STAGE_PRESSURE);
     return SMK_OK;
@@ -894,6 +951,9 @@ int smk_destroy(smk_sim* s)
     if (!s) return SMK_ERR_ARG;
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
+    if (s->aux_stream) { cudaStreamSynchronize(s->aux_stream); cudaStreamDestroy(s->aux_stream); }
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->ev_snap) cudaEventDestroy(s->ev_snap);
     if (s->ev_copied) cudaEventDestroy(s->ev_copied);
     cudaFree(s->snapshot);
@@ -1147,9 +1207,8 @@ long smk_exchange_count(smk_sim* s) { return s ? s->exchanges : -1; }
 int smk_p2p_presignal(smk_sim* s)
 {
     if (!s || !s->p2p) return SMK_ERR_ARG;
-    unsigned* theirs[2] = {nullptr, nullptr};
-    for (int side = 0; side < 2; side++)
-        if (s->peer[side].arena) theirs[side] = reinterpret_cast<unsigned*>(s->peer[side].arena + s->peer[side].lay.counters) + (1 - side) * 32;
+    unsigned* theirs[2]; const unsigned* mine[2];
+    peer_counters(s, theirs, mine);
     smk::k_epoch_signal<<<1, 1, 0, s->stream>>>(theirs[0], theirs[1], s->epoch + 1);
     s->launches++;
     CK(s, cudaGetLastError());
