@@ -477,6 +477,8 @@ int launch_fused_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_
     // SMK_FUSED_CFG selects the older shared-memory kernel (warps x rows per warp) for experiments
     static const int cfg = getenv("SMK_FUSED_CFG") ? atoi(getenv("SMK_FUSED_CFG")) : 0;
     if (K == 4 && cfg == 0) return launch_reg_pass<4, 16>(s, sweep0, out_lo, out_hi, from_peers);
+    if (K == 4 && cfg == 24) return launch_reg_pass<4, 24>(s, sweep0, out_lo, out_hi, from_peers);
+    if (K == 4 && cfg == 12) return launch_reg_pass<4, 12>(s, sweep0, out_lo, out_hi, from_peers);
     switch (cfg) {
     case 163: return launch_fused_pass_cfg<K, 16, 3>(s, sweep0);
     case 124: return launch_fused_pass_cfg<K, 12, 4>(s, sweep0);
