@@ -174,6 +174,24 @@ def time_cpu(scene, budget_s, steps=None, warmup=0):
     return W * H * Ds * steps / dt, cores, kind, sample, dt / steps * 1e3
 
 
+def time_reference_gpu(scene, ticks=10):
+    """The reference's OWN kernels (unmodified smokeSimulation.cu built headless for sm_100a, oracle/_ref/libref_gpu.so) on
+    the same GPU, kernels only, same scene -- the "beat THAT kernel on the same box" bar of SURVEY.md section 8(d)."""
+    import pyoracle as po
+    if not po.have_ref_gpu() or scene[0] * scene[1] * scene[2] > 600 ** 3:   # the reference overflows int sizes from 812^3
+        return None
+    try:
+        r = po.RefGPU(*scene[:3]); po.setup_scene(r, scene)
+        r.step(0.01); r.step(0.05); r.sync()
+        ms = r.time_kernels(0.05, ticks) / ticks
+        r.close()
+        W, H, D = scene[:3]
+        return {"value": W * H * D / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                "what": "68 launches per step of the reference's kernels, device time by CUDA events, no host round trip"}
+    except Exception as ex:   # pragma: no cover
+        return {"unavailable": str(ex)}
+
+
 def extended_scene(scene, label, world, explicit_workload):
     """N > 1 without an explicit workload: weak scaling (BASELINE configs[4] pattern) -- every GPU keeps the N=1 workload
     as its slab, the domain grows along z; source / obstacle keep their coordinates."""
@@ -391,6 +409,9 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             val, cores, kind, sample, _ = time_cpu(scene, budget_s=20.0)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+            ref_gpu = time_reference_gpu(scene)
+            if ref_gpu:
+                line["reference_gpu_kernels"] = ref_gpu
         print(json.dumps(line), flush=True)
     sim.close()
     if world > 1:
