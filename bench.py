@@ -131,10 +131,14 @@ def cpu_engine():
     return (lambda W, H, D: po.Oracle(W, H, D, contract=0)), "port", po
 
 
-def time_cpu(scene, budget_s, steps=None, warmup=0):
+def time_cpu(scene, budget_s, steps=None, warmup=0, solver=None):
     """Time the CPU implementation on a bounded sample of `scene`: full x,y extent, the first Ds cell planes
     (Ds halved until the estimated run fits `budget_s`).  Returns (voxel-steps/s, cores, kind, sample, ms_per_step)."""
     eng, kind, po = cpu_engine()
+    if solver is not None:   # the Jacobi extension has no reference implementation: time the oracle port of it
+        kind = "port"
+        def eng(W_, H_, D_, _s=solver):
+            e_ = po.Oracle(W_, H_, D_); e_.set_solver(1, _s[1]); return e_
     W, H, D = scene[:3]
     cores = os.cpu_count() or 1
     if kind == "reference":
@@ -231,6 +235,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, help="C1|C2|C3|C4 or NxNxN (default: C2; N>1: C2 extended along z, weak scaling)")
+    ap.add_argument("--solver", default="rbgs", choices=["rbgs", "jacobi"],
+                    help="rbgs = the reference schedule (headline); jacobi = damped-Jacobi extension, not a reference path")
+    ap.add_argument("--iterations", type=int, default=None, help="default 30 (rbgs, cu:797) / 40 (jacobi, BASELINE configs[1])")
     ap.add_argument("--fuse", type=int, default=0, help="half-sweeps fused per pressure launch (0 = library default)")
     ap.add_argument("--ghost", type=int, default=8, help="ghost planes per interior slab side (multi-GPU)")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="multi-GPU halo transport")
@@ -289,7 +296,10 @@ def main():
     else:
         sim = smk.SmokeSim(W, H, D)
     po.setup_scene(sim, scene)
-    sim.set_solver(0, 30, args.fuse)
+    jac = args.solver == "jacobi"
+    iters = args.iterations if args.iterations is not None else (40 if jac else 30)
+    sweeps = iters if jac else 2 * iters          # launches of the unfused solver per step
+    sim.set_solver(1 if jac else 0, iters, args.fuse)
     sim.set_stream(stream.cuda_stream)
     c0, c1 = D * rank // world, D * (rank + 1) // world   # owned cell planes of this rank
     host = torch.empty((c1 - c0, H, W), dtype=torch.float32, pin_memory=True)
@@ -365,13 +375,14 @@ def main():
         per_launch_ms = p_ms / max(p_launches, 1)
         cells = W * H * D
         cells_local = W * H * (c1 - c0)                      # one launch of the dominant kernel covers one slab
-        hs_per_launch = 60 * K / max(p_launches, 1)
+        hs_per_launch = sweeps * K / max(p_launches, 1)
         compulsory_bytes = BYTES_PER_CELL_HALFSWEEP * cells_local   # u,v,w read + written once, 1 B of mask information
         alg_bytes = compulsory_bytes * hs_per_launch                # section 8(d): 25 B per cell and HALF-SWEEP x half-sweeps per launch
         achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
         roofline = {
             "bound": "hbm",
-            "kernel": ("k_pressure_reg<4,16>: 4 red/black SOR half-sweeps per launch (temporal blocking, register-resident u,w)"
+            "kernel": ("k_jacobi: one damped-Jacobi iteration per launch (extension)" if jac else
+                       "k_pressure_reg<4,16>: 4 red/black SOR half-sweeps per launch (temporal blocking, register-resident u,w)"
                        if hs_per_launch > 1.5 else "k_pressure_half: one red/black SOR half-sweep per launch"),
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": TRAFFIC_NCU.get((wname, int(round(hs_per_launch)))) if world == 1 else None,
@@ -388,8 +399,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": label + "; reference schedule RBGS omega=1.9 x30", "grid": [W, H, D], "solver": "rbgs",
-                       "iterations": 30, "fuse": args.fuse, "parallelism": f"zslab{world}", "ghost": args.ghost if world > 1 else 0,
+            "config": {"workload": label + (f"; EXTENSION damped Jacobi (2/3) x{iters}, not a reference path" if jac
+                                            else f"; reference schedule RBGS omega=1.9 x{iters}"),
+                       "grid": [W, H, D], "solver": args.solver, "iterations": iters, "fuse": args.fuse, "parallelism": f"zslab{world}", "ghost": args.ghost if world > 1 else 0,
                        "transport": transport_name,
                        "halo_exchanges_per_step": exchanges / K,
                        "l2": f"state per GPU {(2 * cells_local * 4 + 9 * (W + 1) * (H + 1) * (c1 - c0 + 1) * 4 + 2 * cells_local) / 1e6:.0f} MB "
@@ -407,9 +419,9 @@ def main():
             "roofline": roofline,
         }
         if not args.no_cpu_baseline and world == 1:
-            val, cores, kind, sample, _ = time_cpu(scene, budget_s=20.0)
+            val, cores, kind, sample, _ = time_cpu(scene, budget_s=20.0, solver=("jacobi", iters) if jac else None)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
-            ref_gpu = time_reference_gpu(scene)
+            ref_gpu = None if jac else time_reference_gpu(scene)
             if ref_gpu:
                 line["reference_gpu_kernels"] = ref_gpu
         print(json.dumps(line), flush=True)

@@ -104,6 +104,8 @@ class Oracle(_Engine):
             L.orc_update_object_pos.argtypes = [_vp, C.c_int, _f, _f, _f]
             L.orc_set_params.argtypes = [_vp, _f, _f]
             L.orc_set_iterations.argtypes = [_vp, C.c_int]
+            L.orc_set_solver.argtypes = [_vp, C.c_int]
+            L.orc_jacobi_iteration.argtypes = [_vp, _vp]
             L.orc_step.argtypes = [_vp, _f]
             L.orc_flip.argtypes = [_vp]
             L.orc_fill.argtypes = [_vp]
@@ -151,6 +153,13 @@ class Oracle(_Engine):
     def update_object_pos(self, i, x, y, z): self.lib().orc_update_object_pos(self.h, i, x, y, z)
     def set_params(self, g, a): self.lib().orc_set_params(self.h, g, a)
     def set_iterations(self, n): self.lib().orc_set_iterations(self.h, n)
+    def set_solver(self, variant=0, iterations=30, fuse=0):
+        self.lib().orc_set_solver(self.h, variant); self.lib().orc_set_iterations(self.h, iterations)
+
+    def jacobi_iteration(self):
+        p = np.zeros(self.W * self.H * self.D, dtype=np.float32)
+        self.lib().orc_jacobi_iteration(self.h, p.ctypes.data_as(_vp))
+
     def step(self, dt): self.lib().orc_step(self.h, dt)
     def flip(self): self.lib().orc_flip(self.h)
     def fill(self): self.lib().orc_fill(self.h)

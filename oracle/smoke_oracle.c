@@ -35,6 +35,7 @@ struct smk_oracle {
     int now, past;    /* indexNow = 1, tempIndexPast = 0 at start (cu:707-708) */
     float gravity, alpha;
     int iterations;
+    int solver; /* 0 = red-black SOR (reference), 1 = damped Jacobi (extension) */
     int contract;
     int nobj;
     orc_sphere obj[ORC_MAX_OBJECTS];
@@ -137,6 +138,7 @@ void orc_set_params(smk_oracle* o, float gravity, float buoyancy_alpha)
     o->gravity = gravity; o->alpha = buoyancy_alpha;
 }
 void orc_set_iterations(smk_oracle* o, int iterations) { o->iterations = iterations; }
+void orc_set_solver(smk_oracle* o, int solver) { o->solver = solver; }
 int orc_index_now(const smk_oracle* o) { return o->now; }
 
 void orc_flip(smk_oracle* o) /* cu:777-779 */
@@ -285,6 +287,49 @@ void orc_pressure_halfsweep_r(smk_oracle* o, int offset, int za, int zb)
                 w[iw1] = w[iw1] + p * (float)sz1;
             }
         }
+}
+
+/* EXTENSION without a reference counterpart (SURVEY point 1 / H9; BASELINE configs[1] "Jacobi"): one damped-Jacobi
+ * iteration on the same velocity form.  Every interior fluid cell with a fluid neighbour computes, from the OLD fields,
+ *   p_c = (float)((double)(-div_c / (float)acc_c) * (2.0/3.0))          (div and acc exactly as in the half-sweep)
+ * and every face then receives the correction of BOTH adjacent cells, low-side cell first:
+ *   u[x] = (u[x] - p_c * s(x-1)) + p_(x-1) * s_c      (c = cell x; likewise v, w)
+ * p*s is exact, so the two roundings are the two additions.  Weight 2/3 damps the checkerboard mode (plain
+ * simultaneous application leaves it undamped).  `p` is a caller-provided scratch of W*H*D floats. */
+void orc_jacobi_iteration(smk_oracle* o, float* p)
+{
+    const int W = o->W, H = o->H, D = o->D;
+    float *u = o->u[o->now], *v = o->v[o->now], *w = o->w[o->now];
+    const unsigned char* s = o->s;
+#pragma omp parallel for schedule(static)
+    for (int z = 0; z < D; z++)
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++) {
+                size_t c = cidx(o, x, y, z);
+                p[c] = 0.f;
+                if (x < 1 || y < 1 || z < 1 || x >= W - 1 || y >= H - 1 || z >= D - 1 || !s[c]) continue;
+                int acc = s[cidx(o, x - 1, y, z)] + s[cidx(o, x + 1, y, z)] + s[cidx(o, x, y - 1, z)] + s[cidx(o, x, y + 1, z)] +
+                          s[cidx(o, x, y, z - 1)] + s[cidx(o, x, y, z + 1)];
+                if (acc == 0) continue;
+                size_t f = sidx(o, x, y, z);
+                float div = -u[f] + u[sidx(o, x + 1, y, z)];
+                div = div + -v[f];
+                div = div + v[sidx(o, x, y + 1, z)];
+                div = div + -w[f];
+                div = div + w[sidx(o, x, y, z + 1)];
+                float q = -div / (float)acc;
+                p[c] = (float)((double)q * (2.0 / 3.0));
+            }
+#pragma omp parallel for schedule(static)
+    for (int z = 0; z < D; z++)
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++) {
+                size_t c = cidx(o, x, y, z), f = sidx(o, x, y, z);
+                float sc = (float)s[c], pc = p[c];
+                if (x > 0) { float t = u[f] - pc * (float)s[cidx(o, x - 1, y, z)]; u[f] = t + p[cidx(o, x - 1, y, z)] * sc; }
+                if (y > 0) { float t = v[f] - pc * (float)s[cidx(o, x, y - 1, z)]; v[f] = t + p[cidx(o, x, y - 1, z)] * sc; }
+                if (z > 0) { float t = w[f] - pc * (float)s[cidx(o, x, y, z - 1)]; w[f] = t + p[cidx(o, x, y, z - 1)] * sc; }
+            }
 }
 
 /* cu:409-447.  The 8-point face sums in source order, then /8.  They reach one plane
@@ -469,6 +514,11 @@ void orc_step(smk_oracle* o, float dt)
     orc_fill(o);
     orc_integrate(o, dt);
     orc_clamp(o, dt);
+    if (o->solver == 1) { /* extension: damped Jacobi */
+        float* p = (float*)malloc(o->ncell * sizeof(float));
+        for (int i = 0; i < o->iterations; i++) orc_jacobi_iteration(o, p);
+        free(p);
+    } else
     for (int i = 0; i < o->iterations; i++) {
         orc_pressure_halfsweep(o, 0);
         orc_pressure_halfsweep(o, 1);

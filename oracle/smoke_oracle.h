@@ -48,6 +48,8 @@ int orc_add_source(smk_oracle* o, float x, float y, float z, float r);
 void orc_update_object_pos(smk_oracle* o, int id, float x, float y, float z);
 void orc_set_params(smk_oracle* o, float gravity, float buoyancy_alpha);
 void orc_set_iterations(smk_oracle* o, int iterations); /* reference: 30 (cu:797)            */
+void orc_set_solver(smk_oracle* o, int solver);         /* 0 = RBGS (reference), 1 = damped Jacobi (extension) */
+void orc_jacobi_iteration(smk_oracle* o, float* p_scratch); /* extension, see smoke_oracle.c */
 
 /* one full step, cu:774-819 */
 void orc_step(smk_oracle* o, float dt);

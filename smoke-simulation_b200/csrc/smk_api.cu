@@ -22,6 +22,7 @@
 #include "kernels_pressure_fused.cuh"
 #include "kernels_pressure_reg.cuh"
 #include "kernels_advect_tma.cuh"
+#include "kernels_jacobi.cuh"
 #include "slab_plan.h"
 
 namespace {
@@ -504,9 +505,42 @@ int run_pressure_pass(smk_sim* s, int sweep0, int K, int out_lo = INT32_MIN, int
     return launch_halfsweep(s, sweep0 & 1);
 }
 
+// extension: `iterations` damped-Jacobi iterations (kernels_jacobi.cuh), out of place through the scratch set
+int stage_pressure_jacobi(smk_sim* s)
+{
+    const GridP& g = s->g;
+    const int n = s->now;
+    const int xtiles = (g.W + smk::JTX - 1) / smk::JTX, ytiles = (g.SY + smk::JTY - 1) / smk::JTY;
+    // z chunks: the prologue of a chunk (p of the plane below, first loads: about three plane-times per chunk)
+    // is redundant work; pick the split with the best (wave quantisation x useful planes) product at 2 CTAs per SM
+    int nchunk = 1;
+    {
+        const long slots = 2L * s->num_sms, tiles = (long)xtiles * ytiles;
+        double best = -1.0;
+        for (int nc = 1; nc <= std::max(1, g.nzn / 8); nc++) {
+            const int zc = (g.nzn + nc - 1) / nc;
+            const long ctas = tiles * ((g.nzn + zc - 1) / zc), waves = (ctas + slots - 1) / slots;
+            const double eff = (double)ctas / (double)(waves * slots) * (double)zc / (double)(zc + 3);
+            if (eff > best + 1e-9) { best = eff; nchunk = nc; }
+        }
+    }
+    const int zchunk = (g.nzn + nchunk - 1) / nchunk;
+    nchunk = (g.nzn + zchunk - 1) / zchunk;
+    dim3 block(smk::JTHREADS), grid(xtiles, ytiles, nchunk);
+    for (int it = 0; it < s->iterations; it++) {
+        smk::k_jacobi<<<grid, block, 0, s->stream>>>(g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1],
+                                                    s->scratch[2], s->code, zchunk, xtiles);
+        count_launch(s, SMK_STAGE_PRESSURE);
+        swap_in_scratch(s);
+    }
+    CK(s, cudaGetLastError());
+    return SMK_OK;
+}
+
 int stage_pressure(smk_sim* s)
 {
     Span sp(s, SMK_STAGE_PRESSURE);
+    if (s->solver == SMK_SOLVER_JACOBI) return stage_pressure_jacobi(s);
     const int total = 2 * s->iterations;
     const int fuse = effective_fuse(s);
     int done = 0, rc = SMK_OK;
@@ -668,6 +702,8 @@ int exec_op(smk_sim* s, const slab::Op& op, float dt)
     case slab::OP_FORCE: return stage_force_clamp(s, dt, op.a, op.b);
     case slab::OP_PRESSURE: {
         Span sp(s, SMK_STAGE_PRESSURE);
+        // the Jacobi extension (single GPU, so the plan holds no exchange) runs whole at the plan's first pressure op
+        if (s->solver == SMK_SOLVER_JACOBI) return op.p0 == 0 ? stage_pressure_jacobi(s) : SMK_OK;
         const bool from_peers = peer_passes(s) && op.p1 == 4;
         int rc = from_peers ? run_pressure_pass(s, op.p0, op.p1, op.a, op.b, true) : run_pressure_pass(s, op.p0, op.p1);
         if (rc == SMK_OK) CK(s, cudaGetLastError());
@@ -1025,7 +1061,8 @@ float* smk_buoyancy_ptr(smk_sim* s) { return s ? &s->alpha : nullptr; }
 int smk_set_solver(smk_sim* s, int variant, int iterations, int fuse)
 {
     if (!s || iterations < 0 || fuse < 0) return SMK_ERR_ARG;
-    if (variant != SMK_SOLVER_RBGS) return fail(s, SMK_ERR_ARG, "solver variant not available");
+    if (variant != SMK_SOLVER_RBGS && variant != SMK_SOLVER_JACOBI) return fail(s, SMK_ERR_ARG, "solver variant not available");
+    if (variant == SMK_SOLVER_JACOBI && s->geom.world > 1) return fail(s, SMK_ERR_ARG, "the Jacobi extension is single-GPU only");
     if (fuse != 0 && fuse != 1 && fuse != 2 && fuse != 4) return fail(s, SMK_ERR_ARG, "fuse must be 0, 1, 2 or 4");
     s->solver = variant; s->iterations = iterations; s->fuse = fuse;
     return SMK_OK;

@@ -122,3 +122,30 @@ def test_pressure_reduces_divergence(po):
         e.pressure_halfsweep(0); e.pressure_halfsweep(1)
     d1 = e.max_divergence()
     assert d1 < 0.05 * d0, (d0, d1)
+
+
+def test_jacobi_extension_reduces_divergence_and_is_local(po):
+    """The Jacobi extension (no reference counterpart) is specified by the oracle: check what a pressure iteration must
+    do -- the divergence residual falls, solid faces and boundary faces never move -- and that the whole step runs."""
+    W, H, D = 20, 18, 16
+    st = random_state(po, W, H, D, seed=4)
+    e = po.Oracle(W, H, D)
+    inject(po, e, st)
+    e.flip()
+    before = {k: e.get_field(getattr(po, k.upper()), po.NOW).copy() for k in ("u", "v", "w")}
+    d0 = e.max_divergence()
+    for _ in range(40):
+        e.jacobi_iteration()
+    assert e.max_divergence() < 0.1 * d0
+    m = st["mask"].reshape(D, H, W)
+    u = e.get_field(po.U, po.NOW).reshape(D + 1, H + 1, W + 1)
+    ub = before["u"].reshape(D + 1, H + 1, W + 1)
+    solid_face = (m[:, :, 1:] == 0) | (m[:, :, :-1] == 0)  # u face between cells x-1 | x
+    assert np.array_equal(u[:D, :H, 1:W][solid_face], ub[:D, :H, 1:W][solid_face])
+    assert np.array_equal(u[:, :, 0], ub[:, :, 0]) and np.array_equal(u[:, :, W], ub[:, :, W])
+    f = po.Oracle(16, 16, 16)
+    po.setup_scene(f, po.scaled_scene("C1", 16))
+    f.set_solver(1, 40)
+    for t in range(3):
+        f.step(po.tick_dt(t))
+    assert np.isfinite(f.get_field(po.SMOKE, po.NOW)).all()

@@ -271,3 +271,47 @@ def test_density_to_cuda_array_without_host_round_trip(po, smk):
     assert np.array_equal(out, b.get_field(po.SMOKE, po.PAST))
     L.smk_test_array_destroy(arr)
     a.close()
+
+
+# ---- extension: damped-Jacobi pressure iteration (no reference counterpart; specified by the oracle) --------------
+@pytest.mark.parametrize("dims", [(24, 20, 16), (40, 33, 19), (3, 3, 3), (64, 64, 64), (128, 10, 6), (133, 9, 7), (260, 12, 5), (256, 17, 9)])
+def test_jacobi_stage_matches_oracle(po, smk, dims):
+    W, H, D = dims
+    st = random_state(po, W, H, D, seed=11)
+    a, b = make_pair(po, smk, (W, H, D, -9.82, 3.0, [], []), st)
+    a.flip(); b.flip()
+    a.set_solver(1, 7, 0)
+    a.pressure()
+    for _ in range(7):
+        b.jacobi_iteration()
+    compare(po, a, b, f"{dims} 7 jacobi iterations")
+    a.close()
+
+
+def test_jacobi_tiny_values_match_oracle(po, smk):
+    """Velocities in the denormal range (the decaying front of the iteration): the exact-quotient path for acc = 6."""
+    W, H, D = 33, 18, 12
+    st = random_state(po, W, H, D, seed=2)
+    rng = np.random.default_rng(9)
+    for k in ("u", "v", "w"):
+        st[k] = (st[k] * np.float32(2.0) ** rng.integers(-149, -118, st[k].shape).astype(np.float32)).astype(np.float32)
+    st["mask"][:] = 1
+    a, b = make_pair(po, smk, (W, H, D, -9.82, 3.0, [], []), st)
+    a.flip(); b.flip()
+    a.set_solver(1, 3, 0)
+    a.pressure()
+    for _ in range(3):
+        b.jacobi_iteration()
+    compare(po, a, b, "jacobi, denormal-range fields")
+    a.close()
+
+
+def test_jacobi_full_step_matches_oracle(po, smk):
+    sc = po.scaled_scene("C1", 48)
+    a, b = make_pair(po, smk, sc)
+    a.set_solver(1, 40, 0); b.set_solver(1, 40)
+    for t in range(4):
+        a.step(po.tick_dt(t)); b.step(po.tick_dt(t))
+    compare(po, a, b, "jacobi full step")
+    assert a.max_divergence() == b.max_divergence()
+    a.close()
