@@ -178,6 +178,28 @@ def time_cpu(scene, budget_s, steps=None, warmup=0, solver=None):
     return W * H * Ds * steps / dt, cores, kind, sample, dt / steps * 1e3
 
 
+def bind_to_gpu_numa_node(index):
+    """Multi-rank runs: pin this process (and so the first-touch placement of its pinned readback buffer) to the CPU
+    cores NVML reports as local to its GPU, so that 8 concurrent device->host copies do not all land on one socket's
+    memory.  Best effort; returns the number of cores bound to or None."""
+    if os.environ.get("SMK_BENCH_NO_AFFINITY"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def time_reference_gpu(scene, ticks=10):
     """The reference's OWN kernels (unmodified smokeSimulation.cu built headless for sm_100a, oracle/_ref/libref_gpu.so) on
     the same GPU, kernels only, same scene -- the "beat THAT kernel on the same box" bar of SURVEY.md section 8(d)."""
@@ -261,6 +283,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the smoke step has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -402,7 +425,7 @@ def main():
             "config": {"workload": label + (f"; EXTENSION damped Jacobi (2/3) x{iters}, not a reference path" if jac
                                             else f"; reference schedule RBGS omega=1.9 x{iters}"),
                        "grid": [W, H, D], "solver": args.solver, "iterations": iters, "fuse": args.fuse, "parallelism": f"zslab{world}", "ghost": args.ghost if world > 1 else 0,
-                       "transport": transport_name,
+                       "transport": transport_name, "cpu_affinity_cores": numa,
                        "halo_exchanges_per_step": exchanges / K,
                        "l2": f"state per GPU {(2 * cells_local * 4 + 9 * (W + 1) * (H + 1) * (c1 - c0 + 1) * 4 + 2 * cells_local) / 1e6:.0f} MB "
                              "(> 126 MB L2): inputs larger than L2, no explicit flush"},

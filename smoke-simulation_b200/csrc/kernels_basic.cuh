@@ -75,6 +75,30 @@ __global__ void __launch_bounds__(256) k_fill(GridP g, float* __restrict__ smoke
     }
 }
 
+// Sources only, over the sources' bounding boxes (the steady-state fill: the mask and the stencil codes are a pure
+// function of the obstacle list and are reused until that list -- or the mask itself -- changes).  A cell outside the
+// box |d| < |r| + 1 is never inside the sphere (see in_sphere), so scanning the boxes writes exactly the cells the
+// whole-grid kernel writes.  grid.z = source index x box planes.
+struct SrcBoxes {
+    int lo[SMK_MAX_OBJ][3]; // first cell of every source's box
+    int n[3];               // box extent (max over sources)
+};
+__global__ void __launch_bounds__(256) k_fill_sources(GridP g, float* __restrict__ smoke0, float* __restrict__ smoke1,
+                                                      ObjP o, SrcBoxes b)
+{
+    const int k = blockIdx.z / b.n[2], dz = blockIdx.z - k * b.n[2];
+    const int dx = blockIdx.x * 32 + threadIdx.x, dy = blockIdx.y * 8 + threadIdx.y;
+    if (dx >= b.n[0] || dy >= b.n[1]) return;
+    const int x = b.lo[k][0] + dx, y = b.lo[k][1] + dy, z = b.lo[k][2] + dz;
+    if (x < 1 || y < 1 || z < 1 || x >= g.W - 1 || y >= g.H - 1 || z >= g.D - 1) return;
+    if (z < g.zlo || z >= g.zlo + g.nzc) return;
+    if (in_sphere(x, y, z, o.src[k])) {
+        const long long c = cell_index(g, x, y, z);
+        smoke0[c] = 1.0f;
+        smoke1[c] = 1.0f;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Stencil codes.  Not a reference kernel: it folds the seven mask reads of divergence (cu:365-376)
 // and the "both cells fluid" tests of integrate / advection (cu:321, 534, 564, 594, 623) into one byte

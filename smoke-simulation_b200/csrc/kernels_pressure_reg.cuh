@@ -135,6 +135,15 @@ __device__ __forceinline__ void reg_update(float2& ue, float2& uo, float2& we, f
 struct PeerPlanes {
     const float* u; const float* v; const float* w; // the neighbour's current "in" buffers
     int zlo;                                         // global index of the neighbour's first stored plane
+    const float* smoke;                              // the neighbour's density "now" (first pass with fused forcing)
+};
+// Forcing + max-velocity clamp (integrate cu:315-329, velocityConfinement cu:331-352; arithmetic of k_force_clamp)
+// applied to every node as it is loaded by the FIRST pass of a step: both are pointwise in the node index, so
+// "force everything, then sweep" and "force each node on its way into the sweeps" give the same bits, and the
+// separate read-modify-write of u, v, w disappears.
+struct ForceArgs {
+    const float* smoke; // density "now" (cell layout)
+    float dt, gravity, alpha;
 };
 struct PassRange {
     int out_lo, out_hi;  // node planes this launch writes: [out_lo, out_hi)
@@ -143,11 +152,30 @@ struct PassRange {
     PeerPlanes lower, upper;
 };
 
-template <int K, int NW>
+__device__ __forceinline__ void force_clamp_node(float& u, float& v, float& w, unsigned cd, float d, bool clampable,
+                                                 const ForceArgs& fa)
+{
+    if ((cd & CODE_SELF) && (cd & CODE_SY0)) {
+        const float t = __fmaf_rn(__fmul_rn(d, fa.gravity), fa.dt, __fmul_rn(__fmul_rn(d, fa.alpha), fa.dt));
+        v = __fadd_rn(t, v);
+    }
+    if (clampable) {
+        const float L = __fmaf_rn(w, w, __fmaf_rn(u, u, __fmul_rn(v, v)));
+        const float t = __fmul_rn(L, fa.dt);
+        if (t > 9.0f) {
+            const float k = __fdiv_rn(9.0f, t);
+            u = __fmul_rn(u, k);
+            w = __fmul_rn(w, k);
+            v = __fmul_rn(v, k);
+        }
+    }
+}
+
+template <int K, int NW, bool FORCE>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ vi, const float* __restrict__ wi,
                float* __restrict__ uo, float* __restrict__ vo, float* __restrict__ wo,
-               const unsigned char* __restrict__ code, int sweep0, int zchunk, PassRange pr)
+               const unsigned char* __restrict__ code, int sweep0, int zchunk, PassRange pr, ForceArgs fa)
 {
     using C = RegCfg<K, NW>;
     constexpr int LY = C::LY, RS = C::RS, HO = C::HO, R = C::R, PLS = C::PLS;
@@ -185,16 +213,22 @@ k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ 
         CW[k] = 0;
     }
 
-    float4 pu, pv, pw;
+    float4 pu, pv, pw, pd;
     unsigned pc;
+    const bool dok = FORCE && xg >= 0 && xg <= g.W - 4 && yg >= 0 && yg < g.H; // W % 4 == 0 (host checks)
+    const int doff = dok ? xg + yg * g.W : 0;
     auto prefetch = [&](int z) {
         // source of plane z: the local arrays, or a neighbour's memory for planes outside the owned range
-        const float *su = ui, *sv_ = vi, *sw = wi;
+        const float *su = ui, *sv_ = vi, *sw = wi, *sd = fa.smoke;
         int szlo = g.zlo;
         bool zn = z >= g.zlo && z < g.zlo + g.nzn;
-        if (z < pr.own_lo && pr.lower.u) { su = pr.lower.u; sv_ = pr.lower.v; sw = pr.lower.w; szlo = pr.lower.zlo; zn = z >= szlo; }
-        else if (z > pr.own_hi && pr.upper.u) { su = pr.upper.u; sv_ = pr.upper.v; sw = pr.upper.w; szlo = pr.upper.zlo; zn = z <= g.D; }
+        if (z < pr.own_lo && pr.lower.u) { su = pr.lower.u; sv_ = pr.lower.v; sw = pr.lower.w; sd = pr.lower.smoke; szlo = pr.lower.zlo; zn = z >= szlo; }
+        else if (z > pr.own_hi && pr.upper.u) { su = pr.upper.u; sv_ = pr.upper.v; sw = pr.upper.w; sd = pr.upper.smoke; szlo = pr.upper.zlo; zn = z <= g.D; }
         const bool zc = z >= g.zlo && z < g.zlo + g.nzc;
+        if (FORCE) {
+            pd = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (zn && zc && dok) pd = __ldg(reinterpret_cast<const float4*>(sd + (long long)(z - szlo) * g.cplane + doff));
+        }
         pu = pv = pw = make_float4(0.f, 0.f, 0.f, 0.f);
         pc = 0;
         if (zn && nok) {
@@ -221,6 +255,13 @@ k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ 
         }
         if (t > t1) break;
         // (b) plane t enters: u, w and the code word into ring position 0, v into shared memory
+        if (FORCE) { // first pass of the step: forcing + clamp on the way in
+            const bool cl = yg >= 1 && yg < g.H && t >= 1 && t < g.D; // + 1 <= x < W per node
+            force_clamp_node(pu.x, pv.x, pw.x, pc & 255u, pd.x, cl && xg >= 1 && xg < g.W, fa);
+            force_clamp_node(pu.y, pv.y, pw.y, (pc >> 8) & 255u, pd.y, cl && xg + 1 < g.W, fa);
+            force_clamp_node(pu.z, pv.z, pw.z, (pc >> 16) & 255u, pd.z, cl && xg + 2 < g.W, fa);
+            force_clamp_node(pu.w, pv.w, pw.w, pc >> 24, pd.w, cl && xg + 3 < g.W, fa);
+        }
         UE[0] = make_float2(pu.x, pu.z); UO[0] = make_float2(pu.y, pu.w);
         WE[0] = make_float2(pw.x, pw.z); WO[0] = make_float2(pw.y, pw.w);
         CW[0] = pc;

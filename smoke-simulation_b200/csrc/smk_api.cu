@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -82,6 +83,10 @@ struct smk_sim {
     std::vector<Sphere> objects;
 
     int solver = SMK_SOLVER_RBGS;
+    bool pending_force = false; // forcing + clamp of this step are applied by the first pressure pass (fused)
+    float pending_dt = 0.f;
+    int pending_a = 0, pending_b = 0;
+    bool mask_dirty = true; // the mask / stencil codes on the device do not reflect the current obstacle list yet
     int iterations = 30; // cu:797
     int fuse = 0;
 
@@ -119,6 +124,7 @@ struct smk_sim {
     // copied to the host on a second stream while the next step computes
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_snap = nullptr, ev_copied = nullptr;
+    cudaEvent_t ev_chunk[8] = {}; // chunked blocking readback (enqueue_step)
     float* snapshot = nullptr;
     bool copy_pending = false;
 
@@ -233,17 +239,47 @@ void launch_codes(smk_sim* s)
     count_launch(s, SMK_STAGE_FILL);
 }
 
+// Bounding boxes of the sources (|d| < |r| + 1 per axis, clipped to the interior); false if a launch over them is
+// not possible (non-finite parameters, grid.z limit) -- the caller then scans the whole grid.
+bool source_boxes(const smk_sim* s, const ObjP& o, smk::SrcBoxes& b)
+{
+    const GridP& g = s->g;
+    const int dim[3] = {g.W, g.H, g.D};
+    b.n[0] = b.n[1] = b.n[2] = 0;
+    for (int k = 0; k < o.nsrc; k++) {
+        for (int a = 0; a < 3; a++) {
+            const double c = o.src[k][a], r1 = std::fabs((double)o.src[k][3]) + 1.0;
+            if (!std::isfinite(c) || !std::isfinite(r1)) return false;
+            const double lo = std::max(1.0, std::floor(c - r1)), hi = std::min((double)dim[a] - 2.0, std::ceil(c + r1));
+            b.lo[k][a] = (int)std::min(lo, (double)dim[a]);
+            b.n[a] = std::max(b.n[a], hi >= lo ? (int)(hi - lo) + 1 : 0);
+        }
+    }
+    return (long long)b.n[2] * o.nsrc <= 65535;
+}
+
+// Source + mask fill.  The reference rewrites the mask from the obstacle list on every step (cu:289-313, 714-771); the
+// result is a pure function of that list, so it -- and the stencil codes derived from it -- is recomputed only when
+// the list or the mask changed (s->mask_dirty).  The sources are stamped every step, over their bounding boxes.
 int stage_fill(smk_sim* s)
 {
     const GridP& g = s->g;
     Span sp(s, SMK_STAGE_FILL);
     const ObjP o = pack_objects(s);
+    static const bool always_full = getenv("SMK_FILL_FULL") != nullptr;
     if (g.nzc > 0) {
-        if (o.nsrc > 0 || o.nobs > 0) {
+        smk::SrcBoxes b;
+        const bool dirty = s->mask_dirty || always_full;
+        if ((dirty && o.nobs > 0) || (o.nsrc > 0 && !source_boxes(s, o, b))) {
             smk::k_fill<<<row_grid(g.cplane, g.nzm), 256, 0, s->stream>>>(g, s->smoke[0], s->smoke[1], s->mask, o, g.mzlo);
             count_launch(s, SMK_STAGE_FILL);
+        } else if (o.nsrc > 0 && b.n[0] > 0 && b.n[1] > 0 && b.n[2] > 0) {
+            const dim3 grid((unsigned)((b.n[0] + 31) / 32), (unsigned)((b.n[1] + 7) / 8), (unsigned)(b.n[2] * o.nsrc));
+            smk::k_fill_sources<<<grid, dim3(32, 8), 0, s->stream>>>(g, s->smoke[0], s->smoke[1], o, b);
+            count_launch(s, SMK_STAGE_FILL);
         }
-        launch_codes(s);
+        if (dirty) launch_codes(s);
+        s->mask_dirty = false;
     }
     CK(s, cudaGetLastError());
     return SMK_OK;
@@ -388,7 +424,7 @@ int peer_sync(smk_sim* s)
 
 smk::PeerPlanes peer_planes(const smk_sim* s, int side)
 {
-    smk::PeerPlanes p{nullptr, nullptr, nullptr, 0};
+    smk::PeerPlanes p{nullptr, nullptr, nullptr, 0, nullptr};
     const auto& pe = s->peer[side];
     if (!pe.arena) return p;
     const int id = s->vel_id[s->now]; // same physical buffer on every rank (identical swap history)
@@ -396,6 +432,7 @@ smk::PeerPlanes peer_planes(const smk_sim* s, int side)
     p.v = reinterpret_cast<const float*>(pe.arena + pe.lay.v[id]);
     p.w = reinterpret_cast<const float*>(pe.arena + pe.lay.w[id]);
     p.zlo = pe.geom.zlo;
+    p.smoke = reinterpret_cast<const float*>(pe.arena + pe.lay.smoke[s->now]);
     return p;
 }
 
@@ -408,11 +445,16 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
     using C = smk::RegCfg<K, NW>;
     const GridP& g = s->g;
     static bool configured = false;
-    auto kern = smk::k_pressure_reg<K, NW>;
     if (!configured) {
-        CK(s, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        CK(s, cudaFuncSetAttribute(smk::k_pressure_reg<K, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        CK(s, cudaFuncSetAttribute(smk::k_pressure_reg<K, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         configured = true;
     }
+    // forcing + clamp deferred to this pass (exec_op / stage_pressure): the first pass of the step applies them on load
+    const bool force = s->pending_force;
+    s->pending_force = false;
+    auto kern = force ? smk::k_pressure_reg<K, NW, true> : smk::k_pressure_reg<K, NW, false>;
+    const smk::ForceArgs fa{s->smoke[s->now], s->pending_dt, s->gravity, s->alpha};
     smk::PassRange pr{};
     pr.out_lo = out_lo; pr.out_hi = out_hi;
     pr.own_lo = g.zlo; pr.own_hi = g.zlo + g.nzn - 1; // default: everything stored counts as "own" (local source)
@@ -445,12 +487,12 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
         smk::PassRange pb = pr;
         pb.chunk_first = 0; pb.chunk_step = nchunks - 1;
         kern<<<dim3((unsigned)tx, (unsigned)ty, 2u), C::THREADS, C::SMEM, s->aux_stream>>>(
-            g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk, pb);
+            g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk, pb, fa);
         CK(s, cudaEventRecord(s->ev_join, s->aux_stream));
         smk::PassRange pi = pr;
         pi.chunk_first = 1; pi.chunk_step = 1;
         kern<<<dim3((unsigned)tx, (unsigned)ty, (unsigned)(nchunks - 2)), C::THREADS, C::SMEM, s->stream>>>(
-            g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk, pi);
+            g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk, pi, fa);
         CK(s, cudaStreamWaitEvent(s->stream, s->ev_join, 0));
         s->launches++;
     } else {
@@ -459,7 +501,7 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
             if (rc) return rc;
         }
         kern<<<dim3((unsigned)tx, (unsigned)ty, (unsigned)nchunks), C::THREADS, C::SMEM, s->stream>>>(
-            g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk, pr);
+            g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk, pr, fa);
     }
     swap_in_scratch(s);
     count_launch(s, SMK_STAGE_PRESSURE);
@@ -470,6 +512,19 @@ bool peer_passes(const smk_sim* s) // pressure passes may read the neighbours di
 {
     static const int cfg = getenv("SMK_FUSED_CFG") ? atoi(getenv("SMK_FUSED_CFG")) : 0;
     return s->p2p && s->geom.world > 1 && cfg == 0;
+}
+
+int effective_fuse(const smk_sim* s);
+
+// Forcing + clamp can ride on the first pressure pass when that pass is the K = 4 register kernel and every plane it
+// reads is pre-forcing data: a single GPU, or slabs whose passes read the neighbours directly.  (With the callback
+// transport the ghost planes are exchanged AFTER forcing, so forcing stays a stage of its own there.)
+bool can_fuse_force(const smk_sim* s)
+{
+    static const bool off = getenv("SMK_NO_FUSED_FORCE") != nullptr;
+    static const int cfg = getenv("SMK_FUSED_CFG") ? atoi(getenv("SMK_FUSED_CFG")) : 0;
+    return !off && cfg == 0 && s->solver == SMK_SOLVER_RBGS && effective_fuse(s) == 4 && s->iterations >= 2 &&
+           (s->g.W & 3) == 0 && (s->geom.world == 1 || peer_passes(s));
 }
 
 template <int K>
@@ -699,10 +754,20 @@ int exec_op(smk_sim* s, const slab::Op& op, float dt)
     switch (op.kind) {
     case slab::OP_FLIP: flip(s); return SMK_OK;
     case slab::OP_FILL: return stage_fill(s);
-    case slab::OP_FORCE: return stage_force_clamp(s, dt, op.a, op.b);
+    case slab::OP_FORCE:
+        if (can_fuse_force(s)) { // applied by the first pressure pass on load (kernels_pressure_reg.cuh, ForceArgs)
+            s->pending_force = true; s->pending_dt = dt; s->pending_a = op.a; s->pending_b = op.b;
+            return SMK_OK;
+        }
+        return stage_force_clamp(s, dt, op.a, op.b);
     case slab::OP_PRESSURE: {
         Span sp(s, SMK_STAGE_PRESSURE);
         // the Jacobi extension (single GPU, so the plan holds no exchange) runs whole at the plan's first pressure op
+        if (s->pending_force && !(op.p1 == 4 && s->solver == SMK_SOLVER_RBGS)) { // not the pass that can apply it
+            s->pending_force = false;
+            int rc = stage_force_clamp(s, s->pending_dt, s->pending_a, s->pending_b);
+            if (rc) return rc;
+        }
         if (s->solver == SMK_SOLVER_JACOBI) return op.p0 == 0 ? stage_pressure_jacobi(s) : SMK_OK;
         const bool from_peers = peer_passes(s) && op.p1 == 4;
         int rc = from_peers ? run_pressure_pass(s, op.p0, op.p1, op.a, op.b, true) : run_pressure_pass(s, op.p0, op.p1);
@@ -722,8 +787,43 @@ int enqueue_step(smk_sim* s, float dt, float* density_host, bool pipelined = fal
     int rc = SMK_OK;
     const bool pp = peer_passes(s) && effective_fuse(s) == 4;
     const std::vector<slab::Op> ops = slab::plan_step(s->geom, s->iterations, effective_fuse(s), s->carry, pp);
-    for (size_t i = 0; i < ops.size() && rc == SMK_OK; i++) rc = exec_op(s, ops[i], dt);
+    // Blocking readback: the density advection is the last stage and nothing after it reads its output, so it is run
+    // in z-chunks and every finished chunk starts its way to the host on the copy stream while the next one is
+    // computed; the stream of the step then waits for the last copy.
+    static const int split_n = getenv("SMK_READBACK_CHUNKS") ? atoi(getenv("SMK_READBACK_CHUNKS")) : 4;
+    const bool split = density_host && !pipelined && split_n > 1 && !ops.empty() && ops.back().kind == slab::OP_ADVECT_SMOKE &&
+                       ops.back().b - ops.back().a >= 8 * split_n;
+    const size_t nops = split ? ops.size() - 1 : ops.size();
+    for (size_t i = 0; i < nops && rc == SMK_OK; i++) rc = exec_op(s, ops[i], dt);
     if (rc) return rc;
+    if (split) {
+        const GridP& g = s->g;
+        const slab::Op& op = ops.back();
+        const int c0 = s->geom.c0, c1 = s->geom.c1;
+        try_register(s, density_host + (size_t)c0 * g.cplane, (size_t)(c1 - c0) * g.cplane * sizeof(float));
+        if (!s->copy_stream) {
+            CK(s, cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+            CK(s, cudaEventCreateWithFlags(&s->ev_snap, cudaEventDisableTiming));
+            CK(s, cudaEventCreateWithFlags(&s->ev_copied, cudaEventDisableTiming));
+        }
+        if (!s->ev_chunk[0])
+            for (auto& e : s->ev_chunk) CK(s, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        const int nch = std::min(split_n, (int)(sizeof(s->ev_chunk) / sizeof(s->ev_chunk[0])));
+        for (int i = 0; i < nch; i++) {
+            const int a = op.a + (int)((long long)(op.b - op.a) * i / nch), b = op.a + (int)((long long)(op.b - op.a) * (i + 1) / nch);
+            if ((rc = stage_advect_smoke(s, dt, a, b, op.p0, op.p1))) return rc;
+            CK(s, cudaEventRecord(s->ev_chunk[i], s->stream));
+            CK(s, cudaStreamWaitEvent(s->copy_stream, s->ev_chunk[i], 0));
+            // the owned planes outside [op.a, op.b) are boundary planes the advection never writes: they ride along
+            const int pa = i == 0 ? c0 : a, pb = i == nch - 1 ? c1 : b;
+            CK(s, cudaMemcpyAsync(density_host + (size_t)pa * g.cplane, s->smoke[s->past] + (size_t)(pa - g.zlo) * g.cplane,
+                                  (size_t)(pb - pa) * g.cplane * sizeof(float), cudaMemcpyDeviceToHost, s->copy_stream));
+        }
+        Span sp(s, SMK_STAGE_READBACK);
+        CK(s, cudaEventRecord(s->ev_copied, s->copy_stream));
+        CK(s, cudaStreamWaitEvent(s->stream, s->ev_copied, 0));
+        return SMK_OK;
+    }
     if (density_host) { // this slab's OWNED planes of the new density (a single GPU owns everything)
         Span sp(s, SMK_STAGE_READBACK);
         const GridP& g = s->g;
@@ -740,8 +840,8 @@ int enqueue_step(smk_sim* s, float dt, float* density_host, bool pipelined = fal
                 CK(s, cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
                 CK(s, cudaEventCreateWithFlags(&s->ev_snap, cudaEventDisableTiming));
                 CK(s, cudaEventCreateWithFlags(&s->ev_copied, cudaEventDisableTiming));
-                CK(s, cudaMalloc(&s->snapshot, bytes));
             }
+            if (!s->snapshot) CK(s, cudaMalloc(&s->snapshot, bytes));
             if (s->copy_pending) CK(s, cudaStreamWaitEvent(s->stream, s->ev_copied, 0)); // previous snapshot fully on the host
             CK(s, cudaMemcpyAsync(s->snapshot, src, bytes, cudaMemcpyDeviceToDevice, s->stream));
             CK(s, cudaEventRecord(s->ev_snap, s->stream));
@@ -993,6 +1093,7 @@ int smk_destroy(smk_sim* s)
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->ev_snap) cudaEventDestroy(s->ev_snap);
+    for (auto& e : s->ev_chunk) if (e) cudaEventDestroy(e);
     if (s->ev_copied) cudaEventDestroy(s->ev_copied);
     cudaFree(s->snapshot);
     for (void* p : s->registered) cudaHostUnregister(p);
@@ -1035,6 +1136,7 @@ int smk_add_obstacle(smk_sim* s, float x, float y, float z, float vx, float vy, 
     for (auto& o : s->objects) n += o.type == 0;
     if (n >= SMK_MAX_OBJECTS) return -SMK_ERR_LIMIT;
     s->objects.push_back({0, x, y, z, vx, vy, vz, r});
+    s->mask_dirty = true;
     return (int)s->objects.size() - 1;
 }
 
@@ -1052,6 +1154,7 @@ int smk_update_object_pos(smk_sim* s, int id, float x, float y, float z)
 {
     if (!s || id < 0 || id >= (int)s->objects.size()) return SMK_ERR_ARG;
     s->objects[id].x = x; s->objects[id].y = y; s->objects[id].z = z;
+    if (s->objects[id].type == 0) s->mask_dirty = true;
     return SMK_OK;
 }
 
@@ -1187,7 +1290,7 @@ int smk_set_field(smk_sim* s, int field, int which, const void* host_src)
     if (rc) return rc;
     s->carry = slab::initial_carry(s->geom); // injected fields are full-size on every rank: all stored planes valid
     if (field == SMK_FIELD_MASK) { // keep the stencil codes consistent with an injected mask
-        const GridP& g = s->g;
+        s->mask_dirty = true;      // ... and let the next fill apply the obstacle list to it, as the reference would
         launch_codes(s);
         CK(s, cudaGetLastError());
         CK(s, cudaStreamSynchronize(s->stream));

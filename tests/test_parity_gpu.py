@@ -179,6 +179,39 @@ def test_moving_obstacle_and_last_wins(po, smk):
     a.close()
 
 
+def test_sources_by_bounding_box_and_cached_mask(po, smk):
+    """From the second step on the fill stamps the sources over their bounding boxes and reuses mask + stencil codes:
+    spheres partly outside the grid, overlapping, zero / negative / huge radius, non-integer centres, a moving source,
+    and a mask injected between steps (must be re-derived) -- all against the oracle, which fills the whole grid."""
+    W, H, D = 30, 22, 18
+    a = smk.SmokeSim(W, H, D); b = po.Oracle(W, H, D)
+    srcs = [(-2.0, 5.0, 5.0, 4.0), (28.5, 20.25, 16.75, 3.5), (10.0, 10.0, 9.0, 0.0), (12.0, 8.0, 9.0, -2.0),
+            (15.5, 11.5, 9.5, 2.0), (16.0, 12.0, 9.0, 2.5), (100.0, 100.0, 100.0, 3.0)]
+    ids = []
+    for e in (a, b):
+        ids = [e.add_source(*s) for s in srcs]
+        e.add_obstacle(20, 6, 9, 0, 0, 0, 3.0)
+    for t in range(3):
+        a.step(po.tick_dt(t)); b.step(po.tick_dt(t))
+    compare(po, a, b, "sources, step 3")
+    for e in (a, b):
+        e.update_object_pos(ids[4], 7.25, 15.0, 6.5)
+    a.step(0.05); b.step(0.05)
+    compare(po, a, b, "moved source")
+    m = random_state(po, W, H, D, seed=8)["mask"]
+    for e in (a, b):
+        e.set_field(po.MASK, po.NOW, m)
+    a.step(0.05); b.step(0.05)
+    compare(po, a, b, "injected mask, obstacle list re-applied")
+    big = smk.SmokeSim(W, H, D); bo = po.Oracle(W, H, D)
+    for e in (big, bo):
+        e.add_source(15.0, 11.0, 9.0, 500.0)
+    for t in range(2):
+        big.step(po.tick_dt(t)); bo.step(po.tick_dt(t))
+    compare(po, big, bo, "source larger than the grid")
+    a.close(); big.close()
+
+
 def test_empty_scene_and_parameters(po, smk):
     a = smk.SmokeSim(9, 7, 5)
     for t in range(2):
