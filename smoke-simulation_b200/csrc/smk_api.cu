@@ -692,11 +692,9 @@ bool try_register(smk_sim* s, void* p, size_t bytes)
 // halo exchange of one field set through the caller's transport (smk_set_exchange)
 // native halo exchange over peer-mapped memory: handshake, then PULL the neighbours' owned boundary planes into my
 // ghost planes (the neighbour's send region == my receive region, same global planes)
-int run_exchange_p2p(smk_sim* s, int set)
+int p2p_pull(smk_sim* s, int set, cudaStream_t st) // the copies only; the caller has done the handshake
 {
     const GridP& g = s->g;
-    int rc = peer_sync(s);
-    if (rc) return rc;
     for (const slab::Region& r : slab::regions(s->geom, set)) {
         const auto& pe = s->peer[r.side];
         if (!pe.arena || r.recv_n <= 0) continue;
@@ -716,13 +714,20 @@ int run_exchange_p2p(smk_sim* s, int set)
                 src = reinterpret_cast<const float*>(pe.arena + pe.lay.smoke[s->now]) + (size_t)(r.recv_lo - pe.geom.zlo) * plane;
             }
             const unsigned blocks = (unsigned)std::min<size_t>((n16 + 255) / 256, 4 * (size_t)s->num_sms);
-            smk::k_copy16<<<blocks, 256, 0, s->stream>>>(reinterpret_cast<float4*>(dst), reinterpret_cast<const float4*>(src), n16);
+            smk::k_copy16<<<blocks, 256, 0, st>>>(reinterpret_cast<float4*>(dst), reinterpret_cast<const float4*>(src), n16);
             s->launches++;
         }
     }
     s->exchanges++;
     CK(s, cudaGetLastError());
     return SMK_OK;
+}
+
+int run_exchange_p2p(smk_sim* s, int set)
+{
+    int rc = peer_sync(s);
+    if (rc) return rc;
+    return p2p_pull(s, set, s->stream);
 }
 
 int run_exchange(smk_sim* s, int set)
@@ -782,6 +787,43 @@ int exec_op(smk_sim* s, const slab::Op& op, float dt)
 }
 
 // one step = the plan of slab_plan.h executed with CUDA kernels (a single GPU is the 1-slab case: no exchanges)
+// Peer-memory transport: the halo pull in front of the velocity advection hides behind the advection of the planes
+// that need no ghost data.  Publish my epoch; a second stream waits for the neighbours' epoch and pulls their boundary
+// planes (u, v, w and -- if the plan asks for it later in the step -- the density, which has been final since the
+// fill) into my ghost planes; the main stream advects the interior planes meanwhile, then joins and advects the
+// MARGIN planes at each slab end.
+bool overlap_exchange_ok(const smk_sim* s, const slab::Op& adv)
+{
+    static const bool off = getenv("SMK_P2P_NO_OVERLAP") != nullptr;
+    return s->p2p && !off && s->geom.world > 1 && adv.b - adv.a >= 8 + 2 * slab::MARGIN;
+}
+
+int exchange_overlapped_with_advect(smk_sim* s, const slab::Op& adv, float dt, bool with_smoke)
+{
+    int rc;
+    if (!s->aux_stream) {
+        CK(s, cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
+        CK(s, cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+        CK(s, cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+    }
+    if ((rc = peer_signal(s, s->stream))) return rc;
+    CK(s, cudaEventRecord(s->ev_fork, s->stream));
+    CK(s, cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0));
+    if ((rc = peer_wait(s, s->aux_stream))) return rc;
+    if ((rc = p2p_pull(s, slab::SET_VEL_NOW, s->aux_stream))) return rc;
+    if (with_smoke && (rc = p2p_pull(s, slab::SET_SMOKE_NOW, s->aux_stream))) return rc;
+    CK(s, cudaEventRecord(s->ev_join, s->aux_stream));
+    // interior: every plane within MARGIN of an output plane is an owned plane (never written by the pull)
+    const slab::Geom& ge = s->geom;
+    const int lo = ge.has_lower() ? std::max(adv.a, ge.own_node_lo() + slab::MARGIN) : adv.a;
+    const int hi = ge.has_upper() ? std::min(adv.b, ge.own_node_hi() - slab::MARGIN + 1) : adv.b;
+    if ((rc = stage_advect_velocity(s, dt, lo, hi, std::max(adv.p0, ge.own_node_lo()), std::min(adv.p1, ge.own_node_hi())))) return rc;
+    CK(s, cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+    if (lo > adv.a && (rc = stage_advect_velocity(s, dt, adv.a, lo, adv.p0, adv.p1))) return rc;
+    if (adv.b > hi && (rc = stage_advect_velocity(s, dt, hi, adv.b, adv.p0, adv.p1))) return rc;
+    return SMK_OK;
+}
+
 int enqueue_step(smk_sim* s, float dt, float* density_host, bool pipelined = false)
 {
     int rc = SMK_OK;
@@ -794,7 +836,19 @@ int enqueue_step(smk_sim* s, float dt, float* density_host, bool pipelined = fal
     const bool split = density_host && !pipelined && split_n > 1 && !ops.empty() && ops.back().kind == slab::OP_ADVECT_SMOKE &&
                        ops.back().b - ops.back().a >= 8 * split_n;
     const size_t nops = split ? ops.size() - 1 : ops.size();
-    for (size_t i = 0; i < nops && rc == SMK_OK; i++) rc = exec_op(s, ops[i], dt);
+    bool smoke_pulled = false;
+    for (size_t i = 0; i < nops && rc == SMK_OK; i++) {
+        if (ops[i].kind == slab::OP_EXCHANGE && ops[i].a == slab::SET_SMOKE_NOW && smoke_pulled) continue;
+        if (ops[i].kind == slab::OP_EXCHANGE && ops[i].a == slab::SET_VEL_NOW && i + 1 < ops.size() &&
+            ops[i + 1].kind == slab::OP_ADVECT_VEL && overlap_exchange_ok(s, ops[i + 1])) {
+            const bool with_smoke = i + 2 < ops.size() && ops[i + 2].kind == slab::OP_EXCHANGE && ops[i + 2].a == slab::SET_SMOKE_NOW;
+            rc = exchange_overlapped_with_advect(s, ops[i + 1], dt, with_smoke);
+            smoke_pulled = with_smoke;
+            i++; // the advection is done
+            continue;
+        }
+        rc = exec_op(s, ops[i], dt);
+    }
     if (rc) return rc;
     if (split) {
         const GridP& g = s->g;

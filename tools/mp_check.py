@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Multi-process slab check (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/mp_check.py [p2p|nccl] [W H Dper]
+
+Every rank steps its z-slab of a small scene through smk_step (the same call bench.py times) AND the whole grid on its
+own GPU, then compares its owned planes bit for bit: u, v, w (now / past), density (now / past) and the host readback.
+Exit status 0 = every rank identical."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+import pyoracle as po                      # noqa: E402  (scene helpers and field ids only)
+import smoke_simulation_b200 as smk        # noqa: E402
+from conftest import inject, random_state  # noqa: E402
+
+
+def main():
+    transport = sys.argv[1] if len(sys.argv) > 1 else "p2p"
+    W, H, dper = (int(v) for v in sys.argv[2:5]) if len(sys.argv) >= 5 else (64, 48, 40)
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    D, ghost, iterations, steps = dper * world, 8, 7, 4
+    scene = (W, H, D, -9.82, 6.0, [(W / 2, H / 3, D / 2, 5.0), (W / 3, H / 2, dper - 1.0, 4.0)], [(W / 2, H / 2, dper + 0.5, 6.0)])
+    st = random_state(po, W, H, D, seed=17)
+    ref = smk.SmokeSim(W, H, D)
+    sim = smk.SmokeSim(W, H, D, slab=(rank, world), ghost=ghost)
+    for e in (ref, sim):
+        po.setup_scene(e, scene); inject(po, e, st); e.set_solver(0, iterations, 0)
+    keep = None
+    if transport == "p2p":
+        smk.slab.attach_peers_ipc(sim, rank, world, dist, torch.device("cuda", local))
+    else:
+        keep = smk.slab.TorchTransport(rank, world); sim.set_exchange(keep)
+    dist.barrier()
+    host = np.zeros((D, H, W), dtype=np.float32); ref_host = np.zeros_like(host)
+    for t in range(steps):
+        sim.step(po.tick_dt(t), host)
+        ref.step(po.tick_dt(t), ref_host)
+    g = smk.slab.geometry(W, H, D, world, rank, ghost)
+    bad = []
+    for f, name in ((po.U, "u"), (po.V, "v"), (po.W, "w")):
+        for which in (po.NOW, po.PAST):
+            sl = slice(g["own_node_lo"], g["own_node_hi"] + 1)
+            if not np.array_equal(sim.get_field(f, which)[sl], ref.get_field(f, which)[sl]):
+                bad.append((name, which))
+    for which in (po.NOW, po.PAST):
+        if not np.array_equal(sim.get_field(po.SMOKE, which)[g["c0"]:g["c1"]], ref.get_field(po.SMOKE, which)[g["c0"]:g["c1"]]):
+            bad.append(("smoke", which))
+    if not np.array_equal(host[g["c0"]:g["c1"]], ref_host[g["c0"]:g["c1"]]):
+        bad.append(("host readback", 0))
+    ok = torch.tensor([0 if bad else 1], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if bad:
+        print(f"rank {rank}: MISMATCH {bad}", flush=True)
+    if rank == 0:
+        print(f"mp_check {transport} world={world} grid={W}x{H}x{D} exchanges/step={sim.exchange_count() / steps:.1f}:",
+              "OK (bit-identical to the single-GPU run)" if int(ok.item()) else "FAILED", flush=True)
+    sim.close(); ref.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(ok.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
