@@ -145,11 +145,25 @@ struct ForceArgs {
     const float* smoke; // density "now" (cell layout)
     float dt, gravity, alpha;
 };
+// In-kernel handshake of a pass that reads neighbour planes (one launch per pass, no helper kernels or streams):
+// the CTAs of the first / last z-chunk -- the only ones that touch a neighbour's planes -- are scheduled LAST, spin
+// (one thread, acquire loads, clock timeout) until that neighbour has published `wait_epoch`, and the last of them to
+// finish publishes `sig_epoch` into the neighbour's counter: "my boundary planes of this pass are written and I no
+// longer read yours".  Interior CTAs never wait.
+struct PassSync {
+    const unsigned* wait_ctr[2]; // my counters, written by the lower / upper neighbour (nullptr: no neighbour)
+    unsigned* sig_ctr[2];        // the neighbours' counters I publish to
+    unsigned* done_ctr[2];       // local: boundary CTAs of this pass that have finished, per side
+    unsigned wait_epoch, sig_epoch;
+    int* flags;                  // [1] raised on timeout
+    int nchunks;                 // > 0 enables the scheme: block z -> chunk (z + 1) % nchunks
+};
 struct PassRange {
     int out_lo, out_hi;  // node planes this launch writes: [out_lo, out_hi)
     int own_lo, own_hi;  // node planes owned by this slab (inclusive); outside them a peer is the source if present
     int chunk_first, chunk_step; // z-chunk of block z = chunk_first + blockIdx.z * chunk_step (boundary / interior launches)
     PeerPlanes lower, upper;
+    PassSync sync;
 };
 
 __device__ __forceinline__ void force_clamp_node(float& u, float& v, float& w, unsigned cd, float d, bool clampable,
@@ -188,7 +202,27 @@ k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ 
     const int yl = wid + (lane >> 4) * NW;                   // this half-warp's row
     const int x0 = blockIdx.x * C::OX - K;
     const int y0 = blockIdx.y * C::OY - K;
-    const int zo0 = pr.out_lo + (pr.chunk_first + (int)blockIdx.z * pr.chunk_step) * zchunk; // output node planes [zo0, zo1)
+    int chunk = pr.chunk_first + (int)blockIdx.z * pr.chunk_step;
+    int bside = -1; // this CTA reads / serves the neighbour on that side
+    if (pr.sync.nchunks > 0) {
+        chunk = (int)blockIdx.z + 1 < pr.sync.nchunks ? (int)blockIdx.z + 1 : 0; // boundary chunks last
+        if (chunk == 0 && pr.sync.wait_ctr[0]) bside = 0;
+        else if (chunk == pr.sync.nchunks - 1 && pr.sync.wait_ctr[1]) bside = 1;
+        if (bside >= 0) {
+            if (threadIdx.x == 0) {
+                const long long t0c = clock64();
+                unsigned v;
+                do {
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(pr.sync.wait_ctr[bside]) : "memory");
+                    if ((int)(v - pr.sync.wait_epoch) >= 0) break;
+                    if (clock64() - t0c > (long long)2e10) { pr.sync.flags[1] = 1; break; }
+                    __nanosleep(100);
+                } while (true);
+            }
+            __syncthreads();
+        }
+    }
+    const int zo0 = pr.out_lo + chunk * zchunk; // output node planes [zo0, zo1)
     const int zo1 = min(zo0 + zchunk, pr.out_hi);
     const int t0 = zo0 - K, t1 = zo1 + K - 1;                // planes that enter the ring
     const int xg = x0 + 4 * h, yg = y0 + yl;
@@ -311,6 +345,18 @@ k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ 
         // (f) v faces written in this step are read by other rows in the next one
         __syncthreads();
         if (++slot_t == R) slot_t = 0;
+    }
+    if (bside >= 0) { // the last boundary CTA of this side publishes the epoch
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned done = atomicAdd(pr.sync.done_ctr[bside], 1u);
+            if (done == gridDim.x * gridDim.y - 1) {
+                *pr.sync.done_ctr[bside] = 0;
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pr.sync.sig_ctr[bside]), "r"(pr.sync.sig_epoch) : "memory");
+            }
+        }
     }
 }
 

@@ -83,6 +83,7 @@ struct smk_sim {
     std::vector<Sphere> objects;
 
     int solver = SMK_SOLVER_RBGS;
+    int pass_epoch_next = -1;   // half-sweep index whose handshake epoch the previous pass kernel publishes itself
     bool pending_force = false; // forcing + clamp of this step are applied by the first pressure pass (fused)
     float pending_dt = 0.f;
     int pending_a = 0, pending_b = 0;
@@ -469,7 +470,35 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
         pr.own_lo = s->geom.own_node_lo(); pr.own_hi = s->geom.own_node_hi();
         pr.lower = peer_planes(s, 0); pr.upper = peer_planes(s, 1);
     }
-    if (from_peers && overlap && nchunks >= 3 && zchunk >= K) {
+    static const bool inkernel = getenv("SMK_P2P_STREAM_SYNC") == nullptr;
+    if (from_peers && overlap && inkernel && nchunks >= 3 && zchunk >= K) {
+        // One launch per pass, handshake inside the kernel (PassSync): the boundary chunks are scheduled last and wait
+        // for the neighbour's epoch themselves; the last boundary CTA per side publishes mine.  Only the first pass of a
+        // step needs a signal from the stream: it must cover the advection and the fill in front of it.
+        unsigned* theirs[2]; const unsigned* mine[2];
+        peer_counters(s, theirs, mine);
+        // Every pass owns two epoch values: one for a stream-level signal in front of it (published by the first pass
+        // of a step; for the later passes the neighbour's previous pass kernel has already said more) and one that the
+        // kernel publishes when its boundary chunks are done.
+        if (sweep0 == 0 || s->pass_epoch_next != sweep0) {
+            int rc = peer_signal(s, s->stream);
+            if (rc) return rc;
+            pr.sync.wait_epoch = s->epoch;
+        } else {
+            pr.sync.wait_epoch = s->epoch; // the previous pass kernel's own epoch
+            s->epoch++;                    // this pass's stream-level slot stays unused
+        }
+        unsigned* local = reinterpret_cast<unsigned*>(s->arena + s->lay.counters);
+        pr.sync.wait_ctr[0] = mine[0]; pr.sync.wait_ctr[1] = mine[1];
+        pr.sync.sig_ctr[0] = theirs[0]; pr.sync.sig_ctr[1] = theirs[1];
+        pr.sync.done_ctr[0] = local + 64; pr.sync.done_ctr[1] = local + 96;
+        pr.sync.sig_epoch = ++s->epoch;
+        pr.sync.flags = s->d_flags;
+        pr.sync.nchunks = nchunks;
+        s->pass_epoch_next = sweep0 + K;
+        kern<<<dim3((unsigned)tx, (unsigned)ty, (unsigned)nchunks), C::THREADS, C::SMEM, s->stream>>>(
+            g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk, pr, fa);
+    } else if (from_peers && overlap && nchunks >= 3 && zchunk >= K) {
         // The first and last z-chunk read neighbour planes; the interior chunks do not and never write planes a
         // neighbour may still be reading.  So: publish my epoch, start the interior chunks at once on the main stream, and
         // run the two boundary chunks on a second stream behind the epoch wait -- the handshake latency and the skew
