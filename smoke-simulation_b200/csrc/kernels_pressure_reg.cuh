@@ -33,7 +33,8 @@ struct RegCfg {
     static constexpr int HO = 34;
     static constexpr int R = K + 1;            // ring depth
     static constexpr int PLS = (LY + 1) * RS;  // floats per shared v plane (one dummy row)
-    static constexpr int OX = LX - 2 * K, OY = LY - 2 * K;
+    static constexpr int HX = (K + 3) / 4 * 4; // x halo: K rounded up to whole quads (the output region starts on a quad)
+    static constexpr int OX = LX - 2 * HX, OY = LY - 2 * K;
     static constexpr int THREADS = NW * 32;
     static constexpr size_t SMEM = (size_t)R * PLS * sizeof(float);
 };
@@ -193,14 +194,14 @@ k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ 
 {
     using C = RegCfg<K, NW>;
     constexpr int LY = C::LY, RS = C::RS, HO = C::HO, R = C::R, PLS = C::PLS;
-    static_assert(K % 4 == 0 && NW % 2 == 0, "output region starts on a quad; both rows of a warp share the parity");
+    static_assert(K % 2 == 0 && NW % 2 == 0, "a pass is whole red+black pairs; both rows of a warp share the parity");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* sv = reinterpret_cast<float*>(smem_raw); // [R][LY+1][RS]
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int h = lane & 15;                                 // quad index inside the row
     const int yl = wid + (lane >> 4) * NW;                   // this half-warp's row
-    const int x0 = blockIdx.x * C::OX - K;
+    const int x0 = blockIdx.x * C::OX - C::HX;
     const int y0 = blockIdx.y * C::OY - K;
     int chunk = pr.chunk_first + (int)blockIdx.z * pr.chunk_step;
     int bside = -1; // this CTA reads / serves the neighbour on that side
@@ -229,7 +230,7 @@ k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ 
 
     const bool nok = xg >= 0 && xg <= g.P - 4 && yg >= 0 && yg < g.SY;
     const bool kok = xg >= 0 && xg <= g.PC - 4 && yg >= 0 && yg < g.H;
-    const bool sok = nok && yl >= K && yl < LY - K && h >= K / 4 && h < 16 - K / 4;
+    const bool sok = nok && yl >= K && yl < LY - K && h >= C::HX / 4 && h < 16 - C::HX / 4;
     const int noff = nok ? xg + yg * g.P : 0;
     const int koff = kok ? xg + yg * g.PC : 0;
     const int vrow = yl * RS + 2 * h;                        // E[2h] of this lane's row inside a shared v plane

@@ -552,7 +552,7 @@ bool can_fuse_force(const smk_sim* s)
 {
     static const bool off = getenv("SMK_NO_FUSED_FORCE") != nullptr;
     static const int cfg = getenv("SMK_FUSED_CFG") ? atoi(getenv("SMK_FUSED_CFG")) : 0;
-    return !off && cfg == 0 && s->solver == SMK_SOLVER_RBGS && effective_fuse(s) == 4 && s->iterations >= 2 &&
+    return !off && cfg == 0 && s->solver == SMK_SOLVER_RBGS && (effective_fuse(s) == 4 || (effective_fuse(s) == 2 && s->geom.world == 1)) && s->iterations >= 2 &&
            (s->g.W & 3) == 0 && (s->geom.world == 1 || peer_passes(s));
 }
 
@@ -562,6 +562,8 @@ int launch_fused_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_
     // SMK_FUSED_CFG selects the older shared-memory kernel (warps x rows per warp) for experiments
     static const int cfg = getenv("SMK_FUSED_CFG") ? atoi(getenv("SMK_FUSED_CFG")) : 0;
     if (K == 4 && cfg == 0) return launch_reg_pass<4, 16>(s, sweep0, out_lo, out_hi, from_peers);
+    if (K == 2 && cfg == 0) return launch_reg_pass<2, 16>(s, sweep0, out_lo, out_hi, false);
+    if (K == 2 && cfg == 20) return launch_reg_pass<2, 20>(s, sweep0, out_lo, out_hi, false);
     if (K == 4 && cfg == 24) return launch_reg_pass<4, 24>(s, sweep0, out_lo, out_hi, from_peers);
     if (K == 4 && cfg == 12) return launch_reg_pass<4, 12>(s, sweep0, out_lo, out_hi, from_peers);
     switch (cfg) {
@@ -797,7 +799,7 @@ int exec_op(smk_sim* s, const slab::Op& op, float dt)
     case slab::OP_PRESSURE: {
         Span sp(s, SMK_STAGE_PRESSURE);
         // the Jacobi extension (single GPU, so the plan holds no exchange) runs whole at the plan's first pressure op
-        if (s->pending_force && !(op.p1 == 4 && s->solver == SMK_SOLVER_RBGS)) { // not the pass that can apply it
+        if (s->pending_force && !((op.p1 == 4 || op.p1 == 2) && s->solver == SMK_SOLVER_RBGS)) { // not the pass that can apply it
             s->pending_force = false;
             int rc = stage_force_clamp(s, s->pending_dt, s->pending_a, s->pending_b);
             if (rc) return rc;
