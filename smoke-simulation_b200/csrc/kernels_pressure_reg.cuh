@@ -147,17 +147,18 @@ struct ForceArgs {
     float dt, gravity, alpha;
 };
 // In-kernel handshake of a pass that reads neighbour planes (one launch per pass, no helper kernels or streams):
-// the CTAs of the first / last z-chunk -- the only ones that touch a neighbour's planes -- are scheduled LAST, spin
+// the CTAs of the first / last z-chunk -- the only ones that touch a neighbour's planes -- are scheduled FIRST, spin
 // (one thread, acquire loads, clock timeout) until that neighbour has published `wait_epoch`, and the last of them to
 // finish publishes `sig_epoch` into the neighbour's counter: "my boundary planes of this pass are written and I no
-// longer read yours".  Interior CTAs never wait.
+// longer read yours".  Interior CTAs never wait.  (A kernel only ever waits for kernels enqueued before it.)
 struct PassSync {
     const unsigned* wait_ctr[2]; // my counters, written by the lower / upper neighbour (nullptr: no neighbour)
     unsigned* sig_ctr[2];        // the neighbours' counters I publish to
     unsigned* done_ctr[2];       // local: boundary CTAs of this pass that have finished, per side
     unsigned wait_epoch, sig_epoch;
     int* flags;                  // [1] raised on timeout
-    int nchunks;                 // > 0 enables the scheme: block z -> chunk (z + 1) % nchunks
+    int nchunks;                 // > 0 enables the scheme
+    int first;                   // 1: block z = 0, 1 are the boundary chunks (default); 0: they come last
 };
 struct PassRange {
     int out_lo, out_hi;  // node planes this launch writes: [out_lo, out_hi)
@@ -206,7 +207,8 @@ k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ 
     int chunk = pr.chunk_first + (int)blockIdx.z * pr.chunk_step;
     int bside = -1; // this CTA reads / serves the neighbour on that side
     if (pr.sync.nchunks > 0) {
-        chunk = (int)blockIdx.z + 1 < pr.sync.nchunks ? (int)blockIdx.z + 1 : 0; // boundary chunks last
+        if (pr.sync.first) chunk = blockIdx.z == 0 ? 0 : blockIdx.z == 1 ? pr.sync.nchunks - 1 : (int)blockIdx.z - 1;
+        else chunk = (int)blockIdx.z + 1 < pr.sync.nchunks ? (int)blockIdx.z + 1 : 0; // boundary chunks last
         if (chunk == 0 && pr.sync.wait_ctr[0]) bside = 0;
         else if (chunk == pr.sync.nchunks - 1 && pr.sync.wait_ctr[1]) bside = 1;
         if (bside >= 0) {

@@ -472,8 +472,8 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
     }
     static const bool inkernel = getenv("SMK_P2P_STREAM_SYNC") == nullptr;
     if (from_peers && overlap && inkernel && nchunks >= 3 && zchunk >= K) {
-        // One launch per pass, handshake inside the kernel (PassSync): the boundary chunks are scheduled last and wait
-        // for the neighbour's epoch themselves; the last boundary CTA per side publishes mine.  Only the first pass of a
+        // One launch per pass, handshake inside the kernel (PassSync): the boundary chunks wait for the neighbour's
+        // epoch themselves; the last boundary CTA per side publishes mine.  Only the first pass of a
         // step needs a signal from the stream: it must cover the advection and the fill in front of it.
         unsigned* theirs[2]; const unsigned* mine[2];
         peer_counters(s, theirs, mine);
@@ -495,6 +495,13 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
         pr.sync.sig_epoch = ++s->epoch;
         pr.sync.flags = s->d_flags;
         pr.sync.nchunks = nchunks;
+        // boundary chunks FIRST: their neighbour reads pay an NVLink round trip per z-step, which then hides behind the
+        // other CTAs instead of forming the tail of the pass, and their epoch is published early in the pass, so the
+        // neighbour's next pass finds it waiting (measured at N=2: 3.07 ms of passes per step, against 3.18 with the
+        // boundary chunks last and 2.92 on a single GPU)
+        static const bool blast = getenv("SMK_P2P_BOUNDARY_LAST") != nullptr, nowait = getenv("SMK_DBG_NOWAIT") != nullptr;
+        pr.sync.first = blast ? 0 : 1;
+        if (nowait) pr.sync.wait_epoch = 0; // timing experiments only (races!)
         s->pass_epoch_next = sweep0 + K;
         kern<<<dim3((unsigned)tx, (unsigned)ty, (unsigned)nchunks), C::THREADS, C::SMEM, s->stream>>>(
             g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk, pr, fa);
