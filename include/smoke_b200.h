@@ -99,6 +99,14 @@ int smk_add_obstacle(smk_sim* s, float x, float y, float z, float vx, float vy, 
 int smk_add_source(smk_sim* s, float x, float y, float z, float r);
 int smk_update_object_pos(smk_sim* s, int id, float x, float y, float z);
 
+/* Extension.  The reference rewrites the mask once per obstacle, so where spheres overlap or follow one
+ * another the LAST obstacle decides (cu:304-310: a cell inside obstacle 0 but outside obstacle 1 ends up fluid).
+ * SMK_OBSTACLES_UNION makes a cell solid when it lies inside ANY obstacle.  Arbitrary voxelised solids: upload a mask
+ * with smk_set_field(SMK_FIELD_MASK, ...) and add no sphere obstacle -- with an empty obstacle list the reference (and
+ * this library) never touches the mask (cu:289-313), so it persists.  Up to SMK_MAX_OBJECTS spheres per type. */
+enum { SMK_OBSTACLES_LAST_WINS = 0, SMK_OBSTACLES_UNION = 1 };
+int smk_set_obstacle_mode(smk_sim* s, int mode);
+
 /* replace getGravity() / getBuoyancy()  (smokeSimulation.cuh:16-17, cu:31-36): stable pointers to
  * library-owned floats that the caller may write between steps; re-read at every step. */
 float* smk_gravity_ptr(smk_sim* s);
@@ -127,6 +135,11 @@ int smk_sync(smk_sim* s);
 /* device pointer to the density produced by the last step, reference layout (W*H*D floats).
  * Replaces the D2H + glTexSubImage3D round trip of cu:814 / boundingBox.cpp:380-385. */
 const float* smk_density_device(smk_sim* s);
+
+/* Extension (opt-in, never used on a parity path): the density of the last step as IEEE binary16
+ * (converted on the device, round to nearest even) into host_half (W*H*D 16-bit values; a slab writes its owned
+ * planes at their global offset).  Half the device->host bytes of smk_step's float readback.  Blocking. */
+int smk_read_density_half(smk_sim* s, void* host_half);
 
 /* Copy the density of the last step into a 3-D CUDA array (cudaArray_t passed as void*; W x H x D, one float
  * channel) on the step's stream -- e.g. the array of the renderer's GL_R32F texture mapped through CUDA-GL interop.

@@ -105,6 +105,7 @@ class Oracle(_Engine):
             L.orc_set_params.argtypes = [_vp, _f, _f]
             L.orc_set_iterations.argtypes = [_vp, C.c_int]
             L.orc_set_solver.argtypes = [_vp, C.c_int]
+            L.orc_set_obstacle_mode.argtypes = [_vp, C.c_int]
             L.orc_jacobi_iteration.argtypes = [_vp, _vp]
             L.orc_step.argtypes = [_vp, _f]
             L.orc_flip.argtypes = [_vp]
@@ -155,6 +156,8 @@ class Oracle(_Engine):
     def set_iterations(self, n): self.lib().orc_set_iterations(self.h, n)
     def set_solver(self, variant=0, iterations=30, fuse=0):
         self.lib().orc_set_solver(self.h, variant); self.lib().orc_set_iterations(self.h, iterations)
+
+    def set_obstacle_mode(self, union_mode): self.lib().orc_set_obstacle_mode(self.h, int(union_mode))
 
     def jacobi_iteration(self):
         p = np.zeros(self.W * self.H * self.D, dtype=np.float32)

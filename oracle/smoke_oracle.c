@@ -36,6 +36,7 @@ struct smk_oracle {
     float gravity, alpha;
     int iterations;
     int solver; /* 0 = red-black SOR (reference), 1 = damped Jacobi (extension) */
+    int obstacle_union; /* 0 = the last obstacle decides (reference, cu:304-310), 1 = solid inside ANY obstacle (extension) */
     int contract;
     int nobj;
     orc_sphere obj[ORC_MAX_OBJECTS];
@@ -139,6 +140,7 @@ void orc_set_params(smk_oracle* o, float gravity, float buoyancy_alpha)
 }
 void orc_set_iterations(smk_oracle* o, int iterations) { o->iterations = iterations; }
 void orc_set_solver(smk_oracle* o, int solver) { o->solver = solver; }
+void orc_set_obstacle_mode(smk_oracle* o, int union_mode) { o->obstacle_union = union_mode; }
 int orc_index_now(const smk_oracle* o) { return o->now; }
 
 void orc_flip(smk_oracle* o) /* cu:777-779 */
@@ -179,7 +181,7 @@ void orc_fill(smk_oracle* o)
                         if (inside) { o->smoke[0][c] = 1.0f; o->smoke[1][c] = 1.0f; }
                     } else {
                         have_obstacle = 1;
-                        sval = inside ? 0 : 1;
+                        sval = inside ? 0 : (o->obstacle_union ? sval : 1); /* reference: the last obstacle decides */
                     }
                 }
                 if (have_obstacle) o->s[c] = sval;

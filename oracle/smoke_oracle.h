@@ -50,6 +50,7 @@ void orc_set_params(smk_oracle* o, float gravity, float buoyancy_alpha);
 void orc_set_iterations(smk_oracle* o, int iterations); /* reference: 30 (cu:797)            */
 void orc_set_solver(smk_oracle* o, int solver);         /* 0 = RBGS (reference), 1 = damped Jacobi (extension) */
 void orc_jacobi_iteration(smk_oracle* o, float* p_scratch); /* extension, see smoke_oracle.c */
+void orc_set_obstacle_mode(smk_oracle* o, int union_mode); /* 0 = last obstacle decides (reference), 1 = union (extension) */
 
 /* one full step, cu:774-819 */
 void orc_step(smk_oracle* o, float dt);

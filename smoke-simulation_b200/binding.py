@@ -74,6 +74,8 @@ def load_library():
     L.smk_buoyancy_ptr.argtypes = [_vp]
     L.smk_buoyancy_ptr.restype = C.POINTER(_f)
     L.smk_set_solver.argtypes = [_vp, _i, _i, _i]
+    L.smk_set_obstacle_mode.argtypes = [_vp, _i]
+    L.smk_read_density_half.argtypes = [_vp, _vp]
     L.smk_step.argtypes = [_vp, _f, _vp]
     L.smk_step_async.argtypes = [_vp, _f, _vp]
     L.smk_sync.argtypes = [_vp]
@@ -190,6 +192,15 @@ class SmokeSim:
 
     def set_params(self, g, a):
         self.gravity, self.buoyancy = g, a
+
+    def read_density_half(self, out=None):
+        """Density of the last step as float16 (opt-in extension N4); `out` = (D, H, W) float16 array or None."""
+        if out is None:
+            out = np.zeros((self.D, self.H, self.W), dtype=np.float16)
+        self._ck(self.L.smk_read_density_half(self.h, out.ctypes.data_as(_vp)))
+        return out
+
+    def set_obstacle_mode(self, union_mode): self._ck(self.L.smk_set_obstacle_mode(self.h, int(union_mode)))
 
     def set_solver(self, variant=0, iterations=30, fuse=0): self._ck(self.L.smk_set_solver(self.h, variant, iterations, fuse))
     def set_stream(self, cuda_stream): self._ck(self.L.smk_set_stream(self.h, cuda_stream))

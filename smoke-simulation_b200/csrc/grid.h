@@ -35,6 +35,7 @@ enum : unsigned {
 #define SMK_MAX_OBJ 16
 struct ObjP {
     int nsrc, nobs;
+    int obstacle_union; // 0: the last obstacle decides (reference), 1: solid inside any obstacle (extension)
     float src[SMK_MAX_OBJ][4]; // x, y, z, r           (cu:721-727)
     float obs[SMK_MAX_OBJ][4]; // x, y, z, r  (the obstacle velocity is never read by a kernel, cu:299-301)
 };

@@ -10,6 +10,7 @@
 // project/smokeSimulation.cu; the pattern is restated at each function).  The compiler can therefore
 // neither contract nor re-associate anything, and results are bit-identical to the reference step.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include "grid.h"
 
@@ -70,7 +71,8 @@ __global__ void __launch_bounds__(256) k_fill(GridP g, float* __restrict__ smoke
     }
     if (o.nobs > 0) {
         unsigned char sv = 1;
-        for (int k = 0; k < o.nobs; k++) sv = in_sphere(x, y, z, o.obs[k]) ? 0 : 1; // the last obstacle decides (cu:304-310)
+        for (int k = 0; k < o.nobs; k++) // the last obstacle decides (cu:304-310) unless the union extension is on
+            sv = in_sphere(x, y, z, o.obs[k]) ? 0 : (o.obstacle_union ? sv : 1);
         mask[mask_index(g, x, y, z)] = sv;
     }
 }
@@ -542,6 +544,19 @@ __global__ void k_epoch_wait(const unsigned* my_counter_a, const unsigned* my_co
 __global__ void __launch_bounds__(256) k_copy16(float4* __restrict__ dst, const float4* __restrict__ src, size_t n16)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// SURVEY 8(f) N4 (opt-in, off for every parity path): the density as IEEE binary16, round-to-nearest-even, for
+// consumers that want half the device->host bytes.  Two cells per thread.
+__global__ void __launch_bounds__(256) k_density_half(const float* __restrict__ in, __half* __restrict__ out, size_t n)
+{
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i + 1 < n) {
+        const float2 v = *reinterpret_cast<const float2*>(in + i);
+        *reinterpret_cast<__half2*>(out + i) = __floats2half2_rn(v.x, v.y);
+    } else if (i < n) {
+        out[i] = __float2half_rn(in[i]);
+    }
 }
 
 } // namespace smk

@@ -87,6 +87,7 @@ struct smk_sim {
     bool pending_force = false; // forcing + clamp of this step are applied by the first pressure pass (fused)
     float pending_dt = 0.f;
     int pending_a = 0, pending_b = 0;
+    int obstacle_union = 0;     // SURVEY N3 extension: 0 = reference semantics (last obstacle decides)
     bool mask_dirty = true; // the mask / stencil codes on the device do not reflect the current obstacle list yet
     int iterations = 30; // cu:797
     int fuse = 0;
@@ -127,6 +128,7 @@ struct smk_sim {
     cudaEvent_t ev_snap = nullptr, ev_copied = nullptr;
     cudaEvent_t ev_chunk[8] = {}; // chunked blocking readback (enqueue_step)
     float* snapshot = nullptr;
+    void* half_stage = nullptr; // binary16 staging buffer of smk_read_density_half
     bool copy_pending = false;
 
     // timing
@@ -216,6 +218,7 @@ dim3 row_grid(long long per_plane, int planes) { return dim3((unsigned)((per_pla
 ObjP pack_objects(const smk_sim* s)
 {
     ObjP o{};
+    o.obstacle_union = s->obstacle_union;
     for (const Sphere& sp : s->objects) {
         if (sp.type == 1 && o.nsrc < SMK_MAX_OBJ) {
             float* d = o.src[o.nsrc++];
@@ -1188,6 +1191,7 @@ int smk_destroy(smk_sim* s)
     for (auto& e : s->ev_chunk) if (e) cudaEventDestroy(e);
     if (s->ev_copied) cudaEventDestroy(s->ev_copied);
     cudaFree(s->snapshot);
+    cudaFree(s->half_stage);
     for (void* p : s->registered) cudaHostUnregister(p);
     for (auto& sp : s->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
     for (auto e : s->free_events) cudaEventDestroy(e);
@@ -1247,6 +1251,14 @@ int smk_update_object_pos(smk_sim* s, int id, float x, float y, float z)
     if (!s || id < 0 || id >= (int)s->objects.size()) return SMK_ERR_ARG;
     s->objects[id].x = x; s->objects[id].y = y; s->objects[id].z = z;
     if (s->objects[id].type == 0) s->mask_dirty = true;
+    return SMK_OK;
+}
+
+int smk_set_obstacle_mode(smk_sim* s, int mode)
+{
+    if (!s || (mode != SMK_OBSTACLES_LAST_WINS && mode != SMK_OBSTACLES_UNION)) return SMK_ERR_ARG;
+    if (mode != s->obstacle_union) s->mask_dirty = true;
+    s->obstacle_union = mode;
     return SMK_OK;
 }
 
@@ -1313,6 +1325,24 @@ int smk_step(smk_sim* s, float dt, float* density_host)
 }
 
 const float* smk_density_device(smk_sim* s) { return s ? s->smoke[s->past] : nullptr; }
+
+// this slab's owned planes of the last step's density as binary16 -- converted on the device
+// (round to nearest even), half the bytes over PCIe.  Blocking.  Never used by the drop-in entry points.
+int smk_read_density_half(smk_sim* s, void* host_half)
+{
+    if (!s || !host_half) return SMK_ERR_ARG;
+    const GridP& g = s->g;
+    const size_t n = (size_t)(s->geom.c1 - s->geom.c0) * g.cplane;
+    if (!s->half_stage) CK(s, cudaMalloc(&s->half_stage, n * 2));
+    const float* src = s->smoke[s->past] + (size_t)(s->geom.c0 - g.zlo) * g.cplane;
+    smk::k_density_half<<<(unsigned)((n / 2 + 256) / 256), 256, 0, s->stream>>>(src, static_cast<__half*>(s->half_stage), n);
+    s->launches++;
+    CK(s, cudaGetLastError());
+    char* dst = static_cast<char*>(host_half) + (size_t)s->geom.c0 * g.cplane * 2;
+    try_register(s, dst, n * 2);
+    CK(s, cudaMemcpyAsync(dst, s->half_stage, n * 2, cudaMemcpyDeviceToHost, s->stream));
+    return smk_sync(s);
+}
 
 // the renderer samples the density as an R32F 3-D texture (boundingBox.cpp:364-385).  With CUDA-GL interop
 // (cudaGraphicsGLRegisterImage on m_gridTex -> cudaGraphicsSubResourceGetMappedArray) the new density goes straight

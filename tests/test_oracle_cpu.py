@@ -149,3 +149,23 @@ def test_jacobi_extension_reduces_divergence_and_is_local(po):
     for t in range(3):
         f.step(po.tick_dt(t))
     assert np.isfinite(f.get_field(po.SMOKE, po.NOW)).all()
+
+
+def test_union_obstacle_extension_is_the_or_of_single_obstacle_masks(po):
+    """N3 extension, specified by the oracle: in union mode a cell is solid iff it is solid for ANY single obstacle
+    (each evaluated with the reference's own last-wins rule, which for one obstacle is just 'inside')."""
+    W, H, D = 22, 18, 16
+    obs = [(7, 9, 8, 3.0), (13, 9, 8, 3.5), (11, 5, 6, 2.0)]
+
+    def mask_for(spheres, union):
+        e = po.Oracle(W, H, D)
+        for s in spheres:
+            e.add_obstacle(s[0], s[1], s[2], 0, 0, 0, s[3])
+        e.set_obstacle_mode(union)
+        e.step(0.01)
+        return e.get_field(po.MASK)
+
+    singles = [mask_for([s], 0) for s in obs]
+    want = np.minimum.reduce(singles)
+    assert np.array_equal(mask_for(obs, 1), want)
+    assert not np.array_equal(mask_for(obs, 0), want)  # the reference rule really differs on this scene

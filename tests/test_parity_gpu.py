@@ -212,6 +212,53 @@ def test_sources_by_bounding_box_and_cached_mask(po, smk):
     a.close(); big.close()
 
 
+def test_union_obstacles_and_uploaded_mask(po, smk):
+    """SURVEY N3 extensions against the oracle: union semantics for overlapping / consecutive obstacles (the reference
+    lets the last one decide), and an uploaded voxel mask that persists when there is no sphere obstacle."""
+    W, H, D = 24, 20, 18
+    a = smk.SmokeSim(W, H, D); b = po.Oracle(W, H, D)
+    for e in (a, b):
+        e.add_source(12, 5, 9, 3.0)
+        e.add_obstacle(8, 10, 9, 0, 0, 0, 3.0)
+        e.add_obstacle(15, 10, 9, 0, 0, 0, 3.0)
+        e.set_obstacle_mode(1)
+    for t in range(3):
+        a.step(po.tick_dt(t)); b.step(po.tick_dt(t))
+    compare(po, a, b, "union obstacles")
+    m = a.get_field(po.MASK)
+    assert m[9, 10, 8] == 0 and m[9, 10, 15] == 0          # both spheres solid (last-wins would free the first)
+    for e in (a, b):
+        e.set_obstacle_mode(0)
+    a.step(0.05); b.step(0.05)
+    compare(po, a, b, "back to the reference semantics")
+    assert a.get_field(po.MASK)[9, 10, 8] == 1
+    a.close()
+    # voxelised solid: no sphere obstacles, mask uploaded once
+    a = smk.SmokeSim(W, H, D); b = po.Oracle(W, H, D)
+    vox = np.ones((D, H, W), dtype=np.uint8); vox[:, 0, :] = 0; vox[6:12, 8:11, 5:19] = 0
+    for e in (a, b):
+        e.add_source(12, 4, 9, 3.0)
+        e.set_field(po.MASK, po.NOW, vox)
+    for t in range(4):
+        a.step(po.tick_dt(t)); b.step(po.tick_dt(t))
+    compare(po, a, b, "uploaded voxel mask")
+    assert np.array_equal(a.get_field(po.MASK), vox)
+    a.close()
+
+
+def test_half_precision_readback_is_the_rounded_density(po, smk):
+    """binary16 readback == round-to-nearest-even of the float density (numpy's conversion)."""
+    sc = po.scaled_scene("C1", 33)
+    a, b = make_pair(po, smk, sc)
+    for t in range(5):
+        a.step(po.tick_dt(t)); b.step(po.tick_dt(t))
+    h = a.read_density_half()
+    want = b.get_field(po.SMOKE, po.PAST).astype(np.float16)
+    assert h.dtype == np.float16 and np.array_equal(h.view(np.uint16), want.view(np.uint16))
+    assert float(h.astype(np.float32).max()) > 0.5
+    a.close()
+
+
 def test_empty_scene_and_parameters(po, smk):
     a = smk.SmokeSim(9, 7, 5)
     for t in range(2):
