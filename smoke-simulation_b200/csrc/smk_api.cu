@@ -678,7 +678,7 @@ int stage_advect_velocity(smk_sim* s, float dt, int za, int zb, int vlo, int vhi
                 g, s->tmap[0][id], s->tmap[1][id], s->tmap[2][id], s->u[n], s->v[n], s->w[n], s->u[p], s->v[p], s->w[p], s->code, dt,
                 za, zb, zchunk, make_int2(vlo, vhi), s->d_flags);
         } else {
-            static const int by = getenv("SMK_ADV_BY") ? atoi(getenv("SMK_ADV_BY")) : 4, bz = getenv("SMK_ADV_BZ") ? atoi(getenv("SMK_ADV_BZ")) : 2;
+            const int by = 4, bz = 2; // block shape is immaterial (issue-bound; measured 32x4x2 .. 32x8x1 within 1 %)
             const dim3 blk(32, by, bz), grd((g.W + 31) / 32, (g.H + by - 1) / by, (zb - za + bz - 1) / bz);
             smk::k_advect_velocity<<<grd, blk, 0, s->stream>>>(
                 g, s->u[n], s->v[n], s->w[n], s->u[p], s->v[p], s->w[p], s->code, dt, za, zb, make_int2(vlo, vhi), s->d_flags);
@@ -698,7 +698,7 @@ int stage_advect_smoke(smk_sim* s, float dt, int za, int zb, int vlo, int vhi)
     za = std::max(za, std::max(1, g.zlo));
     zb = std::min(zb, std::min(g.D - 1, g.zlo + g.nzc));
     if (zb > za) {
-        static const int by = getenv("SMK_ADV_BY") ? atoi(getenv("SMK_ADV_BY")) : 4, bz = getenv("SMK_ADV_BZ") ? atoi(getenv("SMK_ADV_BZ")) : 2;
+        const int by = 4, bz = 2;
         const dim3 blk(32, by, bz), grd((g.W + 31) / 32, (g.H + by - 1) / by, (zb - za + bz - 1) / bz);
         smk::k_advect_smoke<<<grd, blk, 0, s->stream>>>(
             g, s->smoke[n], s->smoke[p], s->u[p], s->v[p], s->w[p], s->code, dt, za, zb, make_int2(vlo, vhi), s->d_flags);
