@@ -201,7 +201,15 @@ k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ 
 
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int h = lane & 15;                                 // quad index inside the row
-    const int yl = wid + (lane >> 4) * NW;                   // this half-warp's row
+    // This half-warp's row.  Trapezoid halo: after sweep s the face rows [s, LY-1-s] of the tile are right, so sweep j is
+    // only needed on the cell rows [j-1, LY-1-j]: row r needs the sweeps j <= min(r+1, LY-1-r).  Both rows of a warp must
+    // share the x parity of the active colour, so the shallow rows are paired with each other -- (0,30) (1,29) (2,28),
+    // needing 1, 2, 3 sweeps -- and those warps skip the sweeps their rows do not need (6 of the 64 warp-sweeps of a
+    // step); (3,31) and the remaining pairs (w, w+12) run all K.  Other configurations keep the plain (w, w+NW) pairing.
+    constexpr bool SKIP = (K == 4 && NW == 16);
+    const int hb = lane >> 4;
+    const int yl = !SKIP ? wid + hb * NW : wid >= 4 ? wid + hb * 12 : hb == 0 ? wid : wid == 3 ? 31 : 30 - wid;
+    const int jmax = (SKIP && wid < 3) ? wid + 1 : K; // deepest sweep this warp's rows need (warp uniform)
     const int x0 = blockIdx.x * C::OX - C::HX;
     const int y0 = blockIdx.y * C::OY - K;
     int chunk = pr.chunk_first + (int)blockIdx.z * pr.chunk_step;
@@ -236,7 +244,7 @@ k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ 
     const int noff = nok ? xg + yg * g.P : 0;
     const int koff = kok ? xg + yg * g.PC : 0;
     const int vrow = yl * RS + 2 * h;                        // E[2h] of this lane's row inside a shared v plane
-    const int rowpar = (y0 + wid + sweep0 + 1) & 1;          // (+ t) = x parity of the active colour, warp uniform
+    const int rowpar = (y0 + yl + sweep0 + 1) & 1;           // (+ t) = x parity of the active colour, warp uniform
 
     for (int i = threadIdx.x; i < R * PLS; i += C::THREADS) sv[i] = 0.f; // dummy entries / dummy row: defined values
     __syncthreads();
@@ -316,7 +324,7 @@ k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ 
         if (par) {
 #pragma unroll
             for (int j = 1; j <= K; j++) {
-                if (t - j >= t0) {
+                if (t - 2 * j + 1 >= t0 && j <= jmax) { // plane t-j needs sweep j only if it lies j-1 planes above t0
                     int sl = slot_t - j; if (sl < 0) sl += R;
                     reg_update<1, RS, HO>(UE[j], UO[j], WE[j], WO[j], WE[j - 1], WO[j - 1], sv, sl * PLS + vrow, CW[j], h);
                 }
@@ -324,7 +332,7 @@ k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ 
         } else {
 #pragma unroll
             for (int j = 1; j <= K; j++) {
-                if (t - j >= t0) {
+                if (t - 2 * j + 1 >= t0 && j <= jmax) { // plane t-j needs sweep j only if it lies j-1 planes above t0
                     int sl = slot_t - j; if (sl < 0) sl += R;
                     reg_update<0, RS, HO>(UE[j], UO[j], WE[j], WO[j], WE[j - 1], WO[j - 1], sv, sl * PLS + vrow, CW[j], h);
                 }
