@@ -85,6 +85,14 @@ int smk_slab_plan(unsigned W, unsigned H, unsigned D, unsigned world, unsigned r
 int smk_slab_regions(unsigned W, unsigned H, unsigned D, unsigned world, unsigned rank, unsigned ghost, int set,
                      int* out5, int max_regions);
 
+/* host-only (no CUDA call): how a fused pressure pass of K (2 or 4) half-sweeps over the node planes [out_lo, out_hi)
+ * of a W x H grid is cut into pieces for `nctas` CTAs of equal cost (csrc/pass_schedule.h; no reference counterpart --
+ * the reference launches one thread per cell, cu:795-801).  pieces4: {tile x, tile y, zo0, zo1} per piece; first:
+ * CTA b works through pieces [first[b], first[b+1]); info4 = {tiles in x, tiles in y, z-steps of the busiest CTA, CTAs used}.
+ * Returns the number of pieces. */
+int smk_pass_schedule(unsigned W, unsigned H, int out_lo, int out_hi, int K, int nctas, int* pieces4, int max_pieces,
+                      int* first, int max_first, int* info4);
+
 /* replaces deleteVolume()  (smokeSimulation.cuh:9, cu:240-248) */
 int smk_destroy(smk_sim* s);
 
@@ -116,6 +124,10 @@ float* smk_buoyancy_ptr(smk_sim* s);
  * fuse = number of half-sweeps fused per kernel launch (temporal blocking); 0 = library default,
  * 1 = one launch per half-sweep.  Results are identical for every fuse value. */
 int smk_set_solver(smk_sim* s, int variant, int iterations, int fuse);
+/* scheduling of the fused pressure passes (no effect on results): nctas > 0 = run every pass as that many CTAs with
+ * balanced piece lists (csrc/pass_schedule.h); 0 = default (one CTA per SM, or the (tile, z-chunk) grid where that is
+ * no slower); -1 = always the (tile, z-chunk) grid. */
+int smk_set_pass_ctas(smk_sim* s, int nctas);
 
 /* ---- the step ---------------------------------------------------------------------------------------- */
 

@@ -65,6 +65,7 @@ def load_library():
     L.smk_slab_geometry.argtypes = [C.c_uint] * 6 + [C.POINTER(_i)]
     L.smk_slab_plan.argtypes = [C.c_uint] * 6 + [_i, _i, _i, C.POINTER(_i), _i]
     L.smk_slab_regions.argtypes = [C.c_uint] * 6 + [_i, C.POINTER(_i), _i]
+    L.smk_pass_schedule.argtypes = [C.c_uint, C.c_uint, _i, _i, _i, _i, C.POINTER(_i), _i, C.POINTER(_i), _i, C.POINTER(_i)]
     L.smk_destroy.argtypes = [_vp]
     L.smk_add_obstacle.argtypes = [_vp] + [_f] * 7
     L.smk_add_source.argtypes = [_vp] + [_f] * 4
@@ -74,6 +75,7 @@ def load_library():
     L.smk_buoyancy_ptr.argtypes = [_vp]
     L.smk_buoyancy_ptr.restype = C.POINTER(_f)
     L.smk_set_solver.argtypes = [_vp, _i, _i, _i]
+    L.smk_set_pass_ctas.argtypes = [_vp, _i]
     L.smk_set_obstacle_mode.argtypes = [_vp, _i]
     L.smk_read_density_half.argtypes = [_vp, _vp]
     L.smk_step.argtypes = [_vp, _f, _vp]
@@ -203,6 +205,7 @@ class SmokeSim:
     def set_obstacle_mode(self, union_mode): self._ck(self.L.smk_set_obstacle_mode(self.h, int(union_mode)))
 
     def set_solver(self, variant=0, iterations=30, fuse=0): self._ck(self.L.smk_set_solver(self.h, variant, iterations, fuse))
+    def set_pass_ctas(self, nctas): self._ck(self.L.smk_set_pass_ctas(self.h, int(nctas)))
     def set_stream(self, cuda_stream): self._ck(self.L.smk_set_stream(self.h, cuda_stream))
 
     # -- the step (cu:774-819)

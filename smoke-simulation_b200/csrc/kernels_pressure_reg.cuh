@@ -187,18 +187,19 @@ __device__ __forceinline__ void force_clamp_node(float& u, float& v, float& w, u
     }
 }
 
+// One PIECE of a pass: the tile (bx, by) marched over the output node planes [zo0, zo1) (K lead-in planes below, K - 1
+// above).  Any split of a pass into pieces gives the same bits (each piece recomputes its own trapezoid halo from the
+// input set), so the callers are free to schedule pieces: k_pressure_reg = one piece per CTA on a (tile, z-chunk) grid,
+// k_pressure_reg_bal = one CTA per SM working through a list of pieces of equal total cost.
 template <int K, int NW, bool FORCE>
-__global__ void __launch_bounds__(NW * 32, 1)
-k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ vi, const float* __restrict__ wi,
-               float* __restrict__ uo, float* __restrict__ vo, float* __restrict__ wo,
-               const unsigned char* __restrict__ code, int sweep0, int zchunk, PassRange pr, ForceArgs fa)
+__device__ __forceinline__ void reg_pass_piece(const GridP& g, const float* __restrict__ ui, const float* __restrict__ vi,
+                                               const float* __restrict__ wi, float* __restrict__ uo, float* __restrict__ vo,
+                                               float* __restrict__ wo, const unsigned char* __restrict__ code, int sweep0,
+                                               const PassRange& pr, const ForceArgs& fa, float* __restrict__ sv, int bx, int by,
+                                               int zo0, int zo1)
 {
     using C = RegCfg<K, NW>;
     constexpr int LY = C::LY, RS = C::RS, HO = C::HO, R = C::R, PLS = C::PLS;
-    static_assert(K % 2 == 0 && NW % 2 == 0, "a pass is whole red+black pairs; both rows of a warp share the parity");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* sv = reinterpret_cast<float*>(smem_raw); // [R][LY+1][RS]
-
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int h = lane & 15;                                 // quad index inside the row
     // This half-warp's row.  Trapezoid halo: after sweep s the face rows [s, LY-1-s] of the tile are right, so sweep j is
@@ -210,31 +211,8 @@ k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ 
     const int hb = lane >> 4;
     const int yl = !SKIP ? wid + hb * NW : wid >= 4 ? wid + hb * 12 : hb == 0 ? wid : wid == 3 ? 31 : 30 - wid;
     const int jmax = (SKIP && wid < 3) ? wid + 1 : K; // deepest sweep this warp's rows need (warp uniform)
-    const int x0 = blockIdx.x * C::OX - C::HX;
-    const int y0 = blockIdx.y * C::OY - K;
-    int chunk = pr.chunk_first + (int)blockIdx.z * pr.chunk_step;
-    int bside = -1; // this CTA reads / serves the neighbour on that side
-    if (pr.sync.nchunks > 0) {
-        if (pr.sync.first) chunk = blockIdx.z == 0 ? 0 : blockIdx.z == 1 ? pr.sync.nchunks - 1 : (int)blockIdx.z - 1;
-        else chunk = (int)blockIdx.z + 1 < pr.sync.nchunks ? (int)blockIdx.z + 1 : 0; // boundary chunks last
-        if (chunk == 0 && pr.sync.wait_ctr[0]) bside = 0;
-        else if (chunk == pr.sync.nchunks - 1 && pr.sync.wait_ctr[1]) bside = 1;
-        if (bside >= 0) {
-            if (threadIdx.x == 0) {
-                const long long t0c = clock64();
-                unsigned v;
-                do {
-                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(pr.sync.wait_ctr[bside]) : "memory");
-                    if ((int)(v - pr.sync.wait_epoch) >= 0) break;
-                    if (clock64() - t0c > (long long)2e10) { pr.sync.flags[1] = 1; break; }
-                    __nanosleep(100);
-                } while (true);
-            }
-            __syncthreads();
-        }
-    }
-    const int zo0 = pr.out_lo + chunk * zchunk; // output node planes [zo0, zo1)
-    const int zo1 = min(zo0 + zchunk, pr.out_hi);
+    const int x0 = bx * C::OX - C::HX;
+    const int y0 = by * C::OY - K;
     const int t0 = zo0 - K, t1 = zo1 + K - 1;                // planes that enter the ring
     const int xg = x0 + 4 * h, yg = y0 + yl;
 
@@ -357,6 +335,43 @@ k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ 
         __syncthreads();
         if (++slot_t == R) slot_t = 0;
     }
+}
+
+template <int K, int NW, bool FORCE>
+__global__ void __launch_bounds__(NW * 32, 1)
+k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ vi, const float* __restrict__ wi,
+               float* __restrict__ uo, float* __restrict__ vo, float* __restrict__ wo,
+               const unsigned char* __restrict__ code, int sweep0, int zchunk, PassRange pr, ForceArgs fa)
+{
+    using C = RegCfg<K, NW>;
+    static_assert(K % 2 == 0 && NW % 2 == 0, "a pass is whole red+black pairs; both rows of a warp share the parity");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sv = reinterpret_cast<float*>(smem_raw); // [R][LY+1][RS]
+
+    int chunk = pr.chunk_first + (int)blockIdx.z * pr.chunk_step;
+    int bside = -1; // this CTA reads / serves the neighbour on that side
+    if (pr.sync.nchunks > 0) {
+        if (pr.sync.first) chunk = blockIdx.z == 0 ? 0 : blockIdx.z == 1 ? pr.sync.nchunks - 1 : (int)blockIdx.z - 1;
+        else chunk = (int)blockIdx.z + 1 < pr.sync.nchunks ? (int)blockIdx.z + 1 : 0; // boundary chunks last
+        if (chunk == 0 && pr.sync.wait_ctr[0]) bside = 0;
+        else if (chunk == pr.sync.nchunks - 1 && pr.sync.wait_ctr[1]) bside = 1;
+        if (bside >= 0) {
+            if (threadIdx.x == 0) {
+                const long long t0c = clock64();
+                unsigned v;
+                do {
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(pr.sync.wait_ctr[bside]) : "memory");
+                    if ((int)(v - pr.sync.wait_epoch) >= 0) break;
+                    if (clock64() - t0c > (long long)2e10) { pr.sync.flags[1] = 1; break; }
+                    __nanosleep(100);
+                } while (true);
+            }
+            __syncthreads();
+        }
+    }
+    const int zo0 = pr.out_lo + chunk * zchunk; // output node planes [zo0, zo1)
+    const int zo1 = min(zo0 + zchunk, pr.out_hi);
+    reg_pass_piece<K, NW, FORCE>(g, ui, vi, wi, uo, vo, wo, code, sweep0, pr, fa, sv, (int)blockIdx.x, (int)blockIdx.y, zo0, zo1);
     if (bside >= 0) { // the last boundary CTA of this side publishes the epoch
         __threadfence();
         __syncthreads();
@@ -368,6 +383,27 @@ k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ 
                 asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pr.sync.sig_ctr[bside]), "r"(pr.sync.sig_epoch) : "memory");
             }
         }
+    }
+}
+
+// Balanced schedule (single GPU, or slabs whose ghost planes are local): ONE CTA per SM, each working through its own
+// list of pieces -- pieces[first[b] .. first[b+1]) = (tile x, tile y, zo0, zo1) -- which the host cuts so that every
+// CTA marches the same number of z-steps (lead-in planes included).  A (tile, z-chunk) grid quantises into waves
+// (275 CTAs on 148 SMs = 2 rounds of 60 steps at 256^3, 24 CTAs of 35 steps at 80^3); equal shares need ~106 and ~12.
+template <int K, int NW, bool FORCE>
+__global__ void __launch_bounds__(NW * 32, 1)
+k_pressure_reg_bal(GridP g, const float* __restrict__ ui, const float* __restrict__ vi, const float* __restrict__ wi,
+                   float* __restrict__ uo, float* __restrict__ vo, float* __restrict__ wo,
+                   const unsigned char* __restrict__ code, int sweep0, PassRange pr, ForceArgs fa,
+                   const int4* __restrict__ pieces, const int* __restrict__ first)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sv = reinterpret_cast<float*>(smem_raw); // [R][LY+1][RS]
+    const int p0 = first[blockIdx.x], p1 = first[blockIdx.x + 1];
+    for (int p = p0; p < p1; p++) {
+        const int4 pc = pieces[p];
+        if (p > p0) __syncthreads(); // the previous piece's last v write-out reads shared memory
+        reg_pass_piece<K, NW, FORCE>(g, ui, vi, wi, uo, vo, wo, code, sweep0, pr, fa, sv, pc.x, pc.y, pc.z, pc.w);
     }
 }
 

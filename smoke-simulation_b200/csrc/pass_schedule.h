@@ -1,0 +1,92 @@
+// pass_schedule.h -- how one fused pressure pass is cut into pieces for the SMs (pure host C++, no CUDA).
+//
+// A pass of K half-sweeps (kernels_pressure_reg.cuh) marches (x,y) tiles along z.  A PIECE = one tile over the output
+// node planes [zo0, zo1); it costs (zo1 - zo0) useful z-steps plus 2K lead-in / lead-out steps, of which the first ones
+// skip their sweeps.  Any partition of (tiles x planes) into pieces gives the same bits, so the partition is purely a
+// scheduling decision:
+//   * a (tile, z-chunk) grid, one piece per CTA (k_pressure_reg): simple, but CTAs quantise into waves over the SMs;
+//   * this header: `nctas` CTAs (one per SM), each with a LIST of pieces of equal total cost (k_pressure_reg_bal).
+// The reference has no counterpart (one thread per cell, cu:795-801); the tests check coverage and balance on the CPU
+// through the host-only entry point smk_pass_schedule.
+#pragma once
+#include <algorithm>
+#include <vector>
+
+namespace sched {
+
+struct Piece { int bx, by, zo0, zo1; };
+
+struct PassSchedule {
+    std::vector<Piece> pieces;
+    std::vector<int> first; // CTA b works through pieces [first[b], first[b+1])
+    int cost = 0;           // z-steps of the busiest CTA
+    int nctas() const { return first.empty() ? 0 : (int)first.size() - 1; }
+};
+
+inline int piece_cost(int planes, int K) { return planes + 2 * K - 2; }
+constexpr int MIN_PLANES = 4; // no piece shorter than this unless the whole range is (lead-in would dominate)
+
+// greedy fill with per-CTA budget C; returns the number of CTAs used (pieces/first filled if out != nullptr)
+inline int fill(int tx, int ty, int lo, int hi, int K, int C, PassSchedule* out)
+{
+    const int minlen = std::min(MIN_PLANES, hi - lo);
+    int ctas = 0, used = 0, maxc = 0;
+    if (out) { out->pieces.clear(); out->first.assign(1, 0); }
+    for (int by = 0; by < ty; by++)
+        for (int bx = 0; bx < tx; bx++) {
+            int z = lo;
+            while (z < hi) {
+                int room = C - used - (2 * K - 2);
+                if (room < std::min(minlen, hi - z) && used > 0) { // close this CTA
+                    maxc = std::max(maxc, used);
+                    ctas++; used = 0;
+                    if (out) out->first.push_back((int)out->pieces.size());
+                    continue;
+                }
+                int len = std::min(hi - z, std::max(room, minlen));
+                const int rem = hi - z - len;
+                if (rem > 0 && rem < minlen) { // do not leave a stub behind: shorten this piece if it stays long enough
+                    if (len - (minlen - rem) >= minlen) len -= minlen - rem;
+                    else len = hi - z;
+                }
+                if (out) out->pieces.push_back(Piece{bx, by, z, z + len});
+                used += piece_cost(len, K);
+                z += len;
+            }
+        }
+    if (used > 0) {
+        maxc = std::max(maxc, used);
+        ctas++;
+        if (out) out->first.push_back((int)out->pieces.size());
+    }
+    if (out) out->cost = maxc;
+    return ctas;
+}
+
+// smallest budget whose greedy fill needs at most `nctas` CTAs
+inline PassSchedule balance_pass(int tx, int ty, int lo, int hi, int K, int nctas)
+{
+    PassSchedule s;
+    if (tx <= 0 || ty <= 0 || hi <= lo || nctas <= 0) { s.first.assign(1, 0); return s; }
+    int a = piece_cost(std::min(MIN_PLANES, hi - lo), K), b = tx * ty * piece_cost(hi - lo, K);
+    while (a < b) {
+        const int m = a + (b - a) / 2;
+        if (fill(tx, ty, lo, hi, K, m, nullptr) <= nctas) b = m; else a = m + 1;
+    }
+    // the stub rule makes the CTA count only ALMOST monotone in the budget: look a little below for a better one
+    int best = b;
+    for (int c = b - 1; c >= std::max(1, b - 8); c--)
+        if (fill(tx, ty, lo, hi, K, c, nullptr) <= nctas) best = c;
+    while (fill(tx, ty, lo, hi, K, best, &s) > nctas) best++; // (never loops in practice; b is feasible)
+    return s;
+}
+
+// z-steps of the busiest SM under the plain (tile, z-chunk) grid with `slots` co-resident CTAs
+inline int grid_cost(int tiles, int nz, int zchunk, int K, int slots)
+{
+    const int nchunks = (nz + zchunk - 1) / zchunk;
+    const long ctas = (long)tiles * nchunks;
+    return (int)((ctas + slots - 1) / slots) * piece_cost(zchunk, K);
+}
+
+} // namespace sched

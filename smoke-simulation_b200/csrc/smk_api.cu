@@ -25,6 +25,7 @@
 #include "kernels_advect_tma.cuh"
 #include "kernels_jacobi.cuh"
 #include "slab_plan.h"
+#include "pass_schedule.h"
 
 namespace {
 
@@ -91,6 +92,7 @@ struct smk_sim {
     bool mask_dirty = true; // the mask / stencil codes on the device do not reflect the current obstacle list yet
     int iterations = 30; // cu:797
     int fuse = 0;
+    int pass_ctas = 0;   // smk_set_pass_ctas
 
     // slab decomposition (single GPU: owns everything, no ghosts); schedule and validity tracking in slab_plan.h
     slab::Geom geom{};
@@ -138,6 +140,14 @@ struct smk_sim {
     long stage_launches[SMK_STAGE_COUNT]{};
     long launches = 0;
 
+    // balanced piece lists of the fused pressure passes (pass_schedule.h), one per (range, K) seen so far
+    struct DevSchedule {
+        int tx, ty, lo, hi, K, nctas;
+        int4* pieces;
+        int* first;
+        int launch_ctas, cost;
+    };
+    std::vector<DevSchedule> schedules;
     std::string err;
 };
 
@@ -440,6 +450,25 @@ smk::PeerPlanes peer_planes(const smk_sim* s, int side)
     return p;
 }
 
+// piece lists of a balanced pass (pass_schedule.h): computed on the host once per (tiles, plane range, K), kept on the
+// device for the life of the simulation (a step alternates between at most a handful of ranges)
+int get_schedule(smk_sim* s, int tx, int ty, int lo, int hi, int K, int nctas, const smk_sim::DevSchedule** out)
+{
+    for (const auto& d : s->schedules)
+        if (d.tx == tx && d.ty == ty && d.lo == lo && d.hi == hi && d.K == K && d.nctas == nctas) { *out = &d; return SMK_OK; }
+    const sched::PassSchedule ps = sched::balance_pass(tx, ty, lo, hi, K, nctas);
+    static_assert(sizeof(sched::Piece) == sizeof(int4), "pieces are uploaded as int4");
+    smk_sim::DevSchedule d{tx, ty, lo, hi, K, nctas, nullptr, nullptr, ps.nctas(), ps.cost};
+    CK(s, cudaMalloc(&d.pieces, std::max<size_t>(1, ps.pieces.size()) * sizeof(int4)));
+    CK(s, cudaMalloc(&d.first, ps.first.size() * sizeof(int)));
+    // (blocking copies from pageable memory: first use only, i.e. during the first step)
+    if (!ps.pieces.empty()) CK(s, cudaMemcpy(d.pieces, ps.pieces.data(), ps.pieces.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    CK(s, cudaMemcpy(d.first, ps.first.data(), ps.first.size() * sizeof(int), cudaMemcpyHostToDevice));
+    s->schedules.push_back(d);
+    *out = &s->schedules.back();
+    return SMK_OK;
+}
+
 // register-resident fused pass (kernels_pressure_reg.cuh): u, w in registers, v in shared memory.
 // [out_lo, out_hi) = node planes to write; with peers attached the planes outside the owned range are read from the
 // neighbours' memory inside the kernel (after an epoch handshake), otherwise from the local ghost planes.
@@ -452,6 +481,8 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
     if (!configured) {
         CK(s, cudaFuncSetAttribute(smk::k_pressure_reg<K, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         CK(s, cudaFuncSetAttribute(smk::k_pressure_reg<K, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        CK(s, cudaFuncSetAttribute(smk::k_pressure_reg_bal<K, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        CK(s, cudaFuncSetAttribute(smk::k_pressure_reg_bal<K, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         configured = true;
     }
     // forcing + clamp deferred to this pass (exec_op / stage_pressure): the first pass of the step applies them on load
@@ -539,8 +570,26 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
             int rc = peer_sync(s);
             if (rc) return rc;
         }
-        kern<<<dim3((unsigned)tx, (unsigned)ty, (unsigned)nchunks), C::THREADS, C::SMEM, s->stream>>>(
-            g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk, pr, fa);
+        // All planes this pass reads are local (single GPU, ghost planes, or handshake done above): no CTA waits for
+        // another, so the pass runs as one CTA per SM with piece lists of equal cost instead of a (tile, z-chunk) grid
+        // that quantises into waves.  SMK_PASS_BALANCED=0 keeps the grid (ablation).
+        static const bool balanced = !(getenv("SMK_PASS_BALANCED") && atoi(getenv("SMK_PASS_BALANCED")) == 0);
+        const smk_sim::DevSchedule* ds = nullptr;
+        if (balanced && nz > 0 && s->pass_ctas >= 0) {
+            int rc = get_schedule(s, tx, ty, out_lo, out_hi, K, s->pass_ctas > 0 ? s->pass_ctas : s->num_sms, &ds);
+            if (rc) return rc;
+            // default: keep the grid where it is no worse (small grids: many short chunks already fill one wave)
+            if (s->pass_ctas == 0 && ds->cost >= sched::grid_cost(tx * ty, nz, zchunk, K, s->num_sms)) ds = nullptr;
+        }
+        if (ds) {
+            auto kb = force ? smk::k_pressure_reg_bal<K, NW, true> : smk::k_pressure_reg_bal<K, NW, false>;
+            kb<<<dim3((unsigned)ds->launch_ctas), C::THREADS, C::SMEM, s->stream>>>(
+                g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, pr, fa, ds->pieces,
+                ds->first);
+        } else {
+            kern<<<dim3((unsigned)tx, (unsigned)ty, (unsigned)nchunks), C::THREADS, C::SMEM, s->stream>>>(
+                g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk, pr, fa);
+        }
     }
     swap_in_scratch(s);
     count_launch(s, SMK_STAGE_PRESSURE);
@@ -1179,6 +1228,23 @@ int smk_slab_regions(unsigned W, unsigned H, unsigned D, unsigned world, unsigne
     return n;
 }
 
+int smk_pass_schedule(unsigned W, unsigned H, int out_lo, int out_hi, int K, int nctas, int* pieces4, int max_pieces, int* first,
+                      int max_first, int* info4)
+{
+    if (K != 2 && K != 4) return -SMK_ERR_ARG;
+    using C = smk::RegCfg<4, 16>; // OX does not depend on K (whole quads); OY does
+    const int OY = C::LY - 2 * K;
+    const int tx = ((int)W + 1 + C::OX - 1) / C::OX, ty = ((int)H + 1 + OY - 1) / OY;
+    const sched::PassSchedule ps = sched::balance_pass(tx, ty, out_lo, out_hi, K, nctas);
+    for (size_t i = 0; i < ps.pieces.size() && pieces4 && (int)i < max_pieces; i++) {
+        pieces4[4 * i] = ps.pieces[i].bx; pieces4[4 * i + 1] = ps.pieces[i].by;
+        pieces4[4 * i + 2] = ps.pieces[i].zo0; pieces4[4 * i + 3] = ps.pieces[i].zo1;
+    }
+    for (size_t i = 0; i < ps.first.size() && first && (int)i < max_first; i++) first[i] = ps.first[i];
+    if (info4) { info4[0] = tx; info4[1] = ty; info4[2] = ps.cost; info4[3] = ps.nctas(); }
+    return (int)ps.pieces.size();
+}
+
 int smk_destroy(smk_sim* s)
 {
     if (!s) return SMK_ERR_ARG;
@@ -1197,6 +1263,7 @@ int smk_destroy(smk_sim* s)
     for (auto e : s->free_events) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++)
         if (s->peer[i].arena && s->peer[i].ipc) cudaIpcCloseMemHandle(s->peer[i].arena);
+    for (auto& d : s->schedules) { cudaFree(d.pieces); cudaFree(d.first); }
     cudaFree(s->arena);
     cudaFree(s->mask); cudaFree(s->code); cudaFree(s->d_scalar); cudaFree(s->d_flags);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
@@ -1272,6 +1339,13 @@ int smk_set_solver(smk_sim* s, int variant, int iterations, int fuse)
     if (variant == SMK_SOLVER_JACOBI && s->geom.world > 1) return fail(s, SMK_ERR_ARG, "the Jacobi extension is single-GPU only");
     if (fuse != 0 && fuse != 1 && fuse != 2 && fuse != 4) return fail(s, SMK_ERR_ARG, "fuse must be 0, 1, 2 or 4");
     s->solver = variant; s->iterations = iterations; s->fuse = fuse;
+    return SMK_OK;
+}
+
+int smk_set_pass_ctas(smk_sim* s, int nctas)
+{
+    if (!s || nctas < -1) return SMK_ERR_ARG;
+    s->pass_ctas = nctas;
     return SMK_OK;
 }
 

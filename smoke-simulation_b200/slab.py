@@ -52,6 +52,24 @@ def plan_p2p(W, H, D, world, rank, ghost, iterations=30, fuse=4, steps=1):
     return [(OP_NAMES[int(r[0])], int(r[1]), int(r[2]), int(r[3]), int(r[4])) for r in a]
 
 
+def pass_schedule(W, H, out_lo, out_hi, K=4, nctas=148):
+    """How a fused pressure pass over the node planes [out_lo, out_hi) is cut into pieces of equal cost for `nctas`
+    CTAs (csrc/pass_schedule.h, host-only): dict(tiles=(tx, ty), cost=z-steps of the busiest CTA,
+    ctas=[[(tile x, tile y, zo0, zo1), ...] per CTA])."""
+    L = binding.load_library()
+    info = (C.c_int * 4)()
+    n = L.smk_pass_schedule(W, H, out_lo, out_hi, K, nctas, None, 0, None, 0, info)
+    if n < 0:
+        raise binding.SmokeError(f"smk_pass_schedule failed ({n})")
+    pieces = (C.c_int * (4 * max(n, 1)))()
+    first = (C.c_int * (int(info[3]) + 1))()
+    L.smk_pass_schedule(W, H, out_lo, out_hi, K, nctas, pieces, n, first, int(info[3]) + 1, info)
+    pc = np.frombuffer(pieces, dtype=np.int32).reshape(-1, 4)[:n]
+    fs = [int(v) for v in first]
+    ctas = [[tuple(int(v) for v in pc[i]) for i in range(fs[b], fs[b + 1])] for b in range(int(info[3]))]
+    return dict(tiles=(int(info[0]), int(info[1])), cost=int(info[2]), ctas=ctas)
+
+
 def regions(W, H, D, world, rank, ghost, set_id):
     """Halo regions of one exchange: [(side, send_lo, send_n, recv_lo, recv_n), ...] in global plane indices."""
     L = binding.load_library()

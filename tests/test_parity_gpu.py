@@ -306,6 +306,37 @@ def test_fused_pressure_passes_identical(po, smk, dims, fuse):
     a.close()
 
 
+@pytest.mark.parametrize("nctas", [-1, 1, 3, 37, 148])
+@pytest.mark.parametrize("dims,fuse", [((130, 100, 70), 4), ((57, 41, 9), 4), ((120, 50, 40), 2)])
+def test_balanced_piece_lists_identical(po, smk, dims, fuse, nctas):
+    """The schedule of a fused pass is free (csrc/pass_schedule.h): the (tile, z-chunk) grid (-1) and balanced piece
+    lists for 1, 3, 37, 148 CTAs -- CTAs that work through several pieces, pieces of a few planes -- give the bits of
+    separate half-sweep launches and of the oracle.  Random mask and fields; the last pass of 7 iterations has K = 2."""
+    W, H, D = dims
+    st = random_state(po, W, H, D, seed=5)
+    scene = (W, H, D, -9.82, 3.0, [], [])
+    a, b = make_pair(po, smk, scene, st)
+    a.set_solver(0, 7, fuse)
+    a.set_pass_ctas(nctas)
+    a.flip(); b.flip(); a.fill(); b.fill()
+    a.pressure()
+    for i in range(7):
+        b.pressure_halfsweep(0); b.pressure_halfsweep(1)
+    compare(po, a, b, f"{dims} fuse={fuse} nctas={nctas}")
+    a.close()
+
+
+def test_balanced_full_steps_with_fused_forcing(po, smk):
+    """Full steps (forcing + clamp riding on the first pass) with balanced piece lists on 5 CTAs vs the oracle."""
+    sc = po.scaled_scene("C1", 64)
+    a, b = make_pair(po, smk, sc)
+    a.set_pass_ctas(5)
+    for t in range(4):
+        a.step(po.tick_dt(t)); b.step(po.tick_dt(t))
+    compare(po, a, b, "C1/64 balanced, 5 CTAs")
+    a.close()
+
+
 def test_fused_full_steps_c1_obstacle(po, smk):
     """C1 (80^3, obstacle) for 5 ticks with the default fused schedule (15 passes of 4) vs the oracle."""
     sc = po.SCENES["C1"]
