@@ -129,16 +129,15 @@ __device__ __forceinline__ float jacobi_face(float f, float pc, float pn, unsign
     return on ? r : f;
 }
 
-__global__ void __launch_bounds__(JTHREADS) k_jacobi(GridP g, const float* __restrict__ ui, const float* __restrict__ vi,
-                                                     const float* __restrict__ wi, float* __restrict__ uo,
-                                                     float* __restrict__ vo, float* __restrict__ wo,
-                                                     const unsigned char* __restrict__ code, int zchunk, int xtiles)
+// One piece of an iteration: the tile (bx, by) over the node planes [za, zb).
+__device__ __forceinline__ void jacobi_piece(const GridP& g, const float* __restrict__ ui, const float* __restrict__ vi,
+                                             const float* __restrict__ wi, float* __restrict__ uo,
+                                             float* __restrict__ vo, float* __restrict__ wo,
+                                             const unsigned char* __restrict__ code, int xtiles, float (*ps)[JTY + 1][JTX],
+                                             float (*pcol)[JTY + 1], int bx, int by, int za, int zb)
 {
-    __shared__ __align__(16) float ps[2][JTY + 1][JTX]; // row 0 = y0-1, row r = y0 + r - 1
-    __shared__ float pcol[2][JTY + 1];                  // p of the cells (x0-1, y0 + r - 1)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int x0 = blockIdx.x * JTX, y0 = blockIdx.y * JTY;
-    const int za = blockIdx.z * zchunk, zb = min(za + zchunk, g.D + 1); // node planes [za, zb)
+    const int x0 = bx * JTX, y0 = by * JTY;
     const bool halo = wid == JTY;
     const int sy = halo ? 0 : wid + 1;
     const int x = x0 + JQ * lane, y = y0 + sy - 1;
@@ -152,7 +151,7 @@ __global__ void __launch_bounds__(JTHREADS) k_jacobi(GridP g, const float* __res
     // third duty, only when W is a multiple of the tile width: the two pad quads x in [W, P) of every row are copied
     // through by the halo warp of the last x tile (they never change, but the output set needs them)
     const int xC = xtiles * JTX + JQ * (lane & 1), yC = y0 + (lane >> 1);
-    const bool copyC = halo && (int)blockIdx.x == xtiles - 1 && xC < g.P && lane < 2 * JTY && yC <= g.H;
+    const bool copyC = halo && bx == xtiles - 1 && xC < g.P && lane < 2 * JTY && yC <= g.H;
 
     long long n = node_index(g, x, max(y, 0), za), kc = code_index(g, min(x, g.W - 1), min(max(y, 0), g.H - 1), min(za, g.D - 1));
     long long nB = 0, kB = 0, nC = 0;
@@ -226,6 +225,35 @@ __global__ void __launch_bounds__(JTHREADS) k_jacobi(GridP g, const float* __res
         nB += g.nplane;
         kB += g.kplane;
         nC += g.nplane;
+    }
+}
+
+// (tile, z-chunk) grid: one piece per CTA
+__global__ void __launch_bounds__(JTHREADS) k_jacobi(GridP g, const float* __restrict__ ui, const float* __restrict__ vi,
+                                                     const float* __restrict__ wi, float* __restrict__ uo,
+                                                     float* __restrict__ vo, float* __restrict__ wo,
+                                                     const unsigned char* __restrict__ code, int zchunk, int xtiles)
+{
+    __shared__ __align__(16) float ps[2][JTY + 1][JTX]; // row 0 = y0-1, row r = y0 + r - 1
+    __shared__ float pcol[2][JTY + 1];                  // p of the cells (x0-1, y0 + r - 1)
+    const int za = blockIdx.z * zchunk, zb = min(za + zchunk, g.D + 1); // node planes [za, zb)
+    jacobi_piece(g, ui, vi, wi, uo, vo, wo, code, xtiles, ps, pcol, (int)blockIdx.x, (int)blockIdx.y, za, zb);
+}
+
+// balanced piece lists (csrc/pass_schedule.h): as many CTAs as fit the GPU at once, equal z-step shares
+__global__ void __launch_bounds__(JTHREADS) k_jacobi_bal(GridP g, const float* __restrict__ ui, const float* __restrict__ vi,
+                                                         const float* __restrict__ wi, float* __restrict__ uo,
+                                                         float* __restrict__ vo, float* __restrict__ wo,
+                                                         const unsigned char* __restrict__ code, int xtiles,
+                                                         const int4* __restrict__ pieces, const int* __restrict__ first)
+{
+    __shared__ __align__(16) float ps[2][JTY + 1][JTX];
+    __shared__ float pcol[2][JTY + 1];
+    const int p0 = first[blockIdx.x], p1 = first[blockIdx.x + 1];
+    for (int p = p0; p < p1; p++) {
+        const int4 pc = pieces[p];
+        if (p > p0) __syncthreads(); // the shared p tiles of the previous piece are still being read
+        jacobi_piece(g, ui, vi, wi, uo, vo, wo, code, xtiles, ps, pcol, pc.x, pc.y, pc.z, pc.w);
     }
 }
 

@@ -23,11 +23,15 @@ struct PassSchedule {
     int nctas() const { return first.empty() ? 0 : (int)first.size() - 1; }
 };
 
-inline int piece_cost(int planes, int K) { return planes + 2 * K - 2; }
+// lead = z-steps a piece spends before its first output plane, counted at the weight of a full step:
+// 2K - 2 for a pass of K half-sweeps (2K lead-in / lead-out steps, the first ones without sweeps), 3 for a Jacobi piece
+inline int pass_lead(int K) { return 2 * K - 2; }
+constexpr int JACOBI_LEAD = 3;
+inline int piece_cost(int planes, int lead) { return planes + lead; }
 constexpr int MIN_PLANES = 4; // no piece shorter than this unless the whole range is (lead-in would dominate)
 
 // greedy fill with per-CTA budget C; returns the number of CTAs used (pieces/first filled if out != nullptr)
-inline int fill(int tx, int ty, int lo, int hi, int K, int C, PassSchedule* out)
+inline int fill(int tx, int ty, int lo, int hi, int lead, int C, PassSchedule* out)
 {
     const int minlen = std::min(MIN_PLANES, hi - lo);
     int ctas = 0, used = 0, maxc = 0;
@@ -36,7 +40,7 @@ inline int fill(int tx, int ty, int lo, int hi, int K, int C, PassSchedule* out)
         for (int bx = 0; bx < tx; bx++) {
             int z = lo;
             while (z < hi) {
-                int room = C - used - (2 * K - 2);
+                int room = C - used - lead;
                 if (room < std::min(minlen, hi - z) && used > 0) { // close this CTA
                     maxc = std::max(maxc, used);
                     ctas++; used = 0;
@@ -50,7 +54,7 @@ inline int fill(int tx, int ty, int lo, int hi, int K, int C, PassSchedule* out)
                     else len = hi - z;
                 }
                 if (out) out->pieces.push_back(Piece{bx, by, z, z + len});
-                used += piece_cost(len, K);
+                used += piece_cost(len, lead);
                 z += len;
             }
         }
@@ -64,29 +68,29 @@ inline int fill(int tx, int ty, int lo, int hi, int K, int C, PassSchedule* out)
 }
 
 // smallest budget whose greedy fill needs at most `nctas` CTAs
-inline PassSchedule balance_pass(int tx, int ty, int lo, int hi, int K, int nctas)
+inline PassSchedule balance(int tx, int ty, int lo, int hi, int lead, int nctas)
 {
     PassSchedule s;
     if (tx <= 0 || ty <= 0 || hi <= lo || nctas <= 0) { s.first.assign(1, 0); return s; }
-    int a = piece_cost(std::min(MIN_PLANES, hi - lo), K), b = tx * ty * piece_cost(hi - lo, K);
+    int a = piece_cost(std::min(MIN_PLANES, hi - lo), lead), b = tx * ty * piece_cost(hi - lo, lead);
     while (a < b) {
         const int m = a + (b - a) / 2;
-        if (fill(tx, ty, lo, hi, K, m, nullptr) <= nctas) b = m; else a = m + 1;
+        if (fill(tx, ty, lo, hi, lead, m, nullptr) <= nctas) b = m; else a = m + 1;
     }
     // the stub rule makes the CTA count only ALMOST monotone in the budget: look a little below for a better one
     int best = b;
     for (int c = b - 1; c >= std::max(1, b - 8); c--)
-        if (fill(tx, ty, lo, hi, K, c, nullptr) <= nctas) best = c;
-    while (fill(tx, ty, lo, hi, K, best, &s) > nctas) best++; // (never loops in practice; b is feasible)
+        if (fill(tx, ty, lo, hi, lead, c, nullptr) <= nctas) best = c;
+    while (fill(tx, ty, lo, hi, lead, best, &s) > nctas) best++; // (never loops in practice; b is feasible)
     return s;
 }
 
 // z-steps of the busiest SM under the plain (tile, z-chunk) grid with `slots` co-resident CTAs
-inline int grid_cost(int tiles, int nz, int zchunk, int K, int slots)
+inline int grid_cost(int tiles, int nz, int zchunk, int lead, int slots)
 {
     const int nchunks = (nz + zchunk - 1) / zchunk;
     const long ctas = (long)tiles * nchunks;
-    return (int)((ctas + slots - 1) / slots) * piece_cost(zchunk, K);
+    return (int)((ctas + slots - 1) / slots) * piece_cost(zchunk, lead);
 }
 
 } // namespace sched

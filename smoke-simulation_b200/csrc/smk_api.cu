@@ -142,7 +142,7 @@ struct smk_sim {
 
     // balanced piece lists of the fused pressure passes (pass_schedule.h), one per (range, K) seen so far
     struct DevSchedule {
-        int tx, ty, lo, hi, K, nctas;
+        int tx, ty, lo, hi, lead, nctas;
         int4* pieces;
         int* first;
         int launch_ctas, cost;
@@ -452,13 +452,13 @@ smk::PeerPlanes peer_planes(const smk_sim* s, int side)
 
 // piece lists of a balanced pass (pass_schedule.h): computed on the host once per (tiles, plane range, K), kept on the
 // device for the life of the simulation (a step alternates between at most a handful of ranges)
-int get_schedule(smk_sim* s, int tx, int ty, int lo, int hi, int K, int nctas, const smk_sim::DevSchedule** out)
+int get_schedule(smk_sim* s, int tx, int ty, int lo, int hi, int lead, int nctas, const smk_sim::DevSchedule** out)
 {
     for (const auto& d : s->schedules)
-        if (d.tx == tx && d.ty == ty && d.lo == lo && d.hi == hi && d.K == K && d.nctas == nctas) { *out = &d; return SMK_OK; }
-    const sched::PassSchedule ps = sched::balance_pass(tx, ty, lo, hi, K, nctas);
+        if (d.tx == tx && d.ty == ty && d.lo == lo && d.hi == hi && d.lead == lead && d.nctas == nctas) { *out = &d; return SMK_OK; }
+    const sched::PassSchedule ps = sched::balance(tx, ty, lo, hi, lead, nctas);
     static_assert(sizeof(sched::Piece) == sizeof(int4), "pieces are uploaded as int4");
-    smk_sim::DevSchedule d{tx, ty, lo, hi, K, nctas, nullptr, nullptr, ps.nctas(), ps.cost};
+    smk_sim::DevSchedule d{tx, ty, lo, hi, lead, nctas, nullptr, nullptr, ps.nctas(), ps.cost};
     CK(s, cudaMalloc(&d.pieces, std::max<size_t>(1, ps.pieces.size()) * sizeof(int4)));
     CK(s, cudaMalloc(&d.first, ps.first.size() * sizeof(int)));
     // (blocking copies from pageable memory: first use only, i.e. during the first step)
@@ -576,10 +576,10 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
         static const bool balanced = !(getenv("SMK_PASS_BALANCED") && atoi(getenv("SMK_PASS_BALANCED")) == 0);
         const smk_sim::DevSchedule* ds = nullptr;
         if (balanced && nz > 0 && s->pass_ctas >= 0) {
-            int rc = get_schedule(s, tx, ty, out_lo, out_hi, K, s->pass_ctas > 0 ? s->pass_ctas : s->num_sms, &ds);
+            int rc = get_schedule(s, tx, ty, out_lo, out_hi, sched::pass_lead(K), s->pass_ctas > 0 ? s->pass_ctas : s->num_sms, &ds);
             if (rc) return rc;
             // default: keep the grid where it is no worse (small grids: many short chunks already fill one wave)
-            if (s->pass_ctas == 0 && ds->cost >= sched::grid_cost(tx * ty, nz, zchunk, K, s->num_sms)) ds = nullptr;
+            if (s->pass_ctas == 0 && ds->cost >= sched::grid_cost(tx * ty, nz, zchunk, sched::pass_lead(K), s->num_sms)) ds = nullptr;
         }
         if (ds) {
             auto kb = force ? smk::k_pressure_reg_bal<K, NW, true> : smk::k_pressure_reg_bal<K, NW, false>;
@@ -672,9 +672,22 @@ int stage_pressure_jacobi(smk_sim* s)
     const int zchunk = (g.nzn + nchunk - 1) / nchunk;
     nchunk = (g.nzn + zchunk - 1) / zchunk;
     dim3 block(smk::JTHREADS), grid(xtiles, ytiles, nchunk);
+    // balanced piece lists (pass_schedule.h) over the CTAs that fit the GPU at once, unless the grid is no worse
+    static const bool balanced = !(getenv("SMK_PASS_BALANCED") && atoi(getenv("SMK_PASS_BALANCED")) == 0);
+    const smk_sim::DevSchedule* ds = nullptr;
+    if (balanced && s->pass_ctas >= 0) {
+        const int slots = 2 * s->num_sms;
+        int rc = get_schedule(s, xtiles, ytiles, 0, g.nzn, sched::JACOBI_LEAD, s->pass_ctas > 0 ? s->pass_ctas : slots, &ds);
+        if (rc) return rc;
+        if (s->pass_ctas == 0 && ds->cost >= sched::grid_cost(xtiles * ytiles, g.nzn, zchunk, sched::JACOBI_LEAD, slots)) ds = nullptr;
+    }
     for (int it = 0; it < s->iterations; it++) {
-        smk::k_jacobi<<<grid, block, 0, s->stream>>>(g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1],
-                                                    s->scratch[2], s->code, zchunk, xtiles);
+        if (ds)
+            smk::k_jacobi_bal<<<dim3((unsigned)ds->launch_ctas), block, 0, s->stream>>>(
+                g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, xtiles, ds->pieces, ds->first);
+        else
+            smk::k_jacobi<<<grid, block, 0, s->stream>>>(g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1],
+                                                        s->scratch[2], s->code, zchunk, xtiles);
         count_launch(s, SMK_STAGE_PRESSURE);
         swap_in_scratch(s);
     }
@@ -1235,7 +1248,7 @@ int smk_pass_schedule(unsigned W, unsigned H, int out_lo, int out_hi, int K, int
     using C = smk::RegCfg<4, 16>; // OX does not depend on K (whole quads); OY does
     const int OY = C::LY - 2 * K;
     const int tx = ((int)W + 1 + C::OX - 1) / C::OX, ty = ((int)H + 1 + OY - 1) / OY;
-    const sched::PassSchedule ps = sched::balance_pass(tx, ty, out_lo, out_hi, K, nctas);
+    const sched::PassSchedule ps = sched::balance(tx, ty, out_lo, out_hi, sched::pass_lead(K), nctas);
     for (size_t i = 0; i < ps.pieces.size() && pieces4 && (int)i < max_pieces; i++) {
         pieces4[4 * i] = ps.pieces[i].bx; pieces4[4 * i + 1] = ps.pieces[i].by;
         pieces4[4 * i + 2] = ps.pieces[i].zo0; pieces4[4 * i + 3] = ps.pieces[i].zo1;

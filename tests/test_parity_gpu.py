@@ -399,6 +399,23 @@ def test_jacobi_stage_matches_oracle(po, smk, dims):
     a.close()
 
 
+@pytest.mark.parametrize("nctas", [-1, 1, 7, 296])
+@pytest.mark.parametrize("dims", [(133, 41, 37), (260, 12, 5), (64, 64, 64)])
+def test_jacobi_balanced_piece_lists_identical(po, smk, dims, nctas):
+    """Jacobi iterations scheduled as a (tile, z-chunk) grid (-1) or as balanced piece lists on 1 / 7 / 296 CTAs."""
+    W, H, D = dims
+    st = random_state(po, W, H, D, seed=12)
+    a, b = make_pair(po, smk, (W, H, D, -9.82, 3.0, [], []), st)
+    a.flip(); b.flip()
+    a.set_solver(1, 5, 0)
+    a.set_pass_ctas(nctas)
+    a.pressure()
+    for _ in range(5):
+        b.jacobi_iteration()
+    compare(po, a, b, f"{dims} jacobi nctas={nctas}")
+    a.close()
+
+
 def test_jacobi_tiny_values_match_oracle(po, smk):
     """Velocities in the denormal range (the decaying front of the iteration): the exact-quotient path for acc = 6."""
     W, H, D = 33, 18, 12
