@@ -399,13 +399,16 @@ def main():
         cells = W * H * D
         cells_local = W * H * (c1 - c0)                      # one launch of the dominant kernel covers one slab
         hs_per_launch = sweeps * K / max(p_launches, 1)
+        bal = sim.last_pass_ctas()
         compulsory_bytes = BYTES_PER_CELL_HALFSWEEP * cells_local   # u,v,w read + written once, 1 B of mask information
         alg_bytes = compulsory_bytes * hs_per_launch                # section 8(d): 25 B per cell and HALF-SWEEP x half-sweeps per launch
         achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
         roofline = {
             "bound": "hbm",
-            "kernel": ("k_jacobi: one damped-Jacobi iteration per launch (extension)" if jac else
-                       "k_pressure_reg<4,16>: 4 red/black SOR half-sweeps per launch (temporal blocking, register-resident u,w)"
+            "kernel": ((f"k_jacobi_bal ({bal} CTAs, balanced piece lists)" if bal else "k_jacobi") +
+                       ": one damped-Jacobi iteration per launch (extension)" if jac else
+                       (f"k_pressure_reg_bal<4,16> ({bal} CTAs, balanced piece lists)" if bal else "k_pressure_reg<4,16>") +
+                       ": 4 red/black SOR half-sweeps per launch (temporal blocking, register-resident u,w)"
                        if hs_per_launch > 1.5 else "k_pressure_half: one red/black SOR half-sweep per launch"),
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": TRAFFIC_NCU.get((wname, int(round(hs_per_launch)))) if world == 1 else None,

@@ -128,6 +128,8 @@ int smk_set_solver(smk_sim* s, int variant, int iterations, int fuse);
  * balanced piece lists (csrc/pass_schedule.h); 0 = default (one CTA per SM, or the (tile, z-chunk) grid where that is
  * no slower); -1 = always the (tile, z-chunk) grid. */
 int smk_set_pass_ctas(smk_sim* s, int nctas);
+/* CTAs of the most recent pressure pass if it ran on balanced piece lists, 0 if it ran as a (tile, z-chunk) grid */
+int smk_last_pass_ctas(smk_sim* s);
 
 /* ---- the step ---------------------------------------------------------------------------------------- */
 

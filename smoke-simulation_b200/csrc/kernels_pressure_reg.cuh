@@ -159,6 +159,7 @@ struct PassSync {
     int* flags;                  // [1] raised on timeout
     int nchunks;                 // > 0 enables the scheme
     int first;                   // 1: block z = 0, 1 are the boundary chunks (default); 0: they come last
+    int npieces[2];              // k_pressure_reg_bal: boundary pieces per side (the last one to finish publishes)
 };
 struct PassRange {
     int out_lo, out_hi;  // node planes this launch writes: [out_lo, out_hi)
@@ -386,10 +387,14 @@ k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ 
     }
 }
 
-// Balanced schedule (single GPU, or slabs whose ghost planes are local): ONE CTA per SM, each working through its own
-// list of pieces -- pieces[first[b] .. first[b+1]) = (tile x, tile y, zo0, zo1) -- which the host cuts so that every
-// CTA marches the same number of z-steps (lead-in planes included).  A (tile, z-chunk) grid quantises into waves
-// (275 CTAs on 148 SMs = 2 rounds of 60 steps at 256^3, 24 CTAs of 35 steps at 80^3); equal shares need ~106 and ~12.
+// Balanced schedule: ONE CTA per SM, each working through its own list of pieces -- pieces[first[b] .. first[b+1]) =
+// (tile x, tile y, zo0, zo1) -- which the host cuts so that every CTA marches the same number of z-steps (lead-in planes
+// included).  A (tile, z-chunk) grid quantises into waves (275 CTAs on 148 SMs = 2 rounds of 58 steps at 256^3); equal
+// shares need 104.
+// Multi-GPU (pr.sync.nchunks > 0): a BOUNDARY piece of a side is one that reads the neighbour's planes, which is exactly
+// when it writes planes the neighbour reads (zo0 - K < own_lo  <=>  zo0 < own_lo + K; likewise above).  The host puts
+// the boundary pieces first in every list; a CTA waits for the neighbour's epoch before its first boundary piece of a
+// side, and the last boundary piece per side to finish publishes this pass's epoch (same protocol as k_pressure_reg).
 template <int K, int NW, bool FORCE>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_pressure_reg_bal(GridP g, const float* __restrict__ ui, const float* __restrict__ vi, const float* __restrict__ wi,
@@ -400,10 +405,49 @@ k_pressure_reg_bal(GridP g, const float* __restrict__ ui, const float* __restric
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* sv = reinterpret_cast<float*>(smem_raw); // [R][LY+1][RS]
     const int p0 = first[blockIdx.x], p1 = first[blockIdx.x + 1];
+    unsigned waited = 0;
     for (int p = p0; p < p1; p++) {
         const int4 pc = pieces[p];
         if (p > p0) __syncthreads(); // the previous piece's last v write-out reads shared memory
+        unsigned side = 0;
+        if (pr.sync.nchunks > 0) {
+            if (pr.sync.wait_ctr[0] && pc.z - K < pr.own_lo) side |= 1u;
+            if (pr.sync.wait_ctr[1] && pc.w + K - 1 > pr.own_hi) side |= 2u;
+            const unsigned need = side & ~waited;
+            if (need) {
+                if (threadIdx.x == 0) {
+                    for (int sd = 0; sd < 2; sd++) {
+                        if (!((need >> sd) & 1u)) continue;
+                        const long long t0c = clock64();
+                        unsigned v;
+                        do {
+                            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(pr.sync.wait_ctr[sd]) : "memory");
+                            if ((int)(v - pr.sync.wait_epoch) >= 0) break;
+                            if (clock64() - t0c > (long long)2e10) { pr.sync.flags[1] = 1; break; }
+                            __nanosleep(100);
+                        } while (true);
+                    }
+                }
+                __syncthreads();
+                waited |= need;
+            }
+        }
         reg_pass_piece<K, NW, FORCE>(g, ui, vi, wi, uo, vo, wo, code, sweep0, pr, fa, sv, pc.x, pc.y, pc.z, pc.w);
+        if (side) {
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int sd = 0; sd < 2; sd++) {
+                    if (!((side >> sd) & 1u)) continue;
+                    const unsigned done = atomicAdd(pr.sync.done_ctr[sd], 1u);
+                    if (done == (unsigned)pr.sync.npieces[sd] - 1u) {
+                        *pr.sync.done_ctr[sd] = 0;
+                        __threadfence_system();
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pr.sync.sig_ctr[sd]), "r"(pr.sync.sig_epoch) : "memory");
+                    }
+                }
+            }
+        }
     }
 }
 

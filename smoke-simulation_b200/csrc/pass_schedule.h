@@ -85,6 +85,23 @@ inline PassSchedule balance(int tx, int ty, int lo, int hi, int lead, int nctas)
     return s;
 }
 
+// Multi-GPU passes that read the neighbours' planes inside the kernel: a piece is a BOUNDARY piece of the lower side
+// if zo0 < zl and of the upper side if zo1 > zh (kernels_pressure_reg.cuh: it reads the neighbour's planes and writes
+// the planes the neighbour reads).  They wait for the neighbour's epoch and the last of them publishes this pass's, so
+// every CTA runs them first: the epoch goes out early in the pass and the waits hide behind the interior pieces of the
+// other CTAs.  Returns the number of boundary pieces per side in counts[2].
+inline void boundary_first(PassSchedule& s, int zl, int zh, int counts[2])
+{
+    counts[0] = counts[1] = 0;
+    for (int b = 0; b + 1 < (int)s.first.size(); b++)
+        std::stable_partition(s.pieces.begin() + s.first[b], s.pieces.begin() + s.first[b + 1],
+                              [&](const Piece& p) { return p.zo0 < zl || p.zo1 > zh; });
+    for (const Piece& p : s.pieces) {
+        if (p.zo0 < zl) counts[0]++;
+        if (p.zo1 > zh) counts[1]++;
+    }
+}
+
 // z-steps of the busiest SM under the plain (tile, z-chunk) grid with `slots` co-resident CTAs
 inline int grid_cost(int tiles, int nz, int zchunk, int lead, int slots)
 {

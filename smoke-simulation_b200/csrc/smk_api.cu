@@ -93,6 +93,7 @@ struct smk_sim {
     int iterations = 30; // cu:797
     int fuse = 0;
     int pass_ctas = 0;   // smk_set_pass_ctas
+    int last_pass_ctas = 0; // CTAs of the last balanced pass launch (0: it was a (tile, z-chunk) grid)
 
     // slab decomposition (single GPU: owns everything, no ghosts); schedule and validity tracking in slab_plan.h
     slab::Geom geom{};
@@ -142,10 +143,11 @@ struct smk_sim {
 
     // balanced piece lists of the fused pressure passes (pass_schedule.h), one per (range, K) seen so far
     struct DevSchedule {
-        int tx, ty, lo, hi, lead, nctas;
+        int tx, ty, lo, hi, lead, nctas, zl, zh; // zl / zh: boundary-piece limits (INT_MIN / INT_MAX: none)
         int4* pieces;
         int* first;
         int launch_ctas, cost;
+        int nboundary[2];
     };
     std::vector<DevSchedule> schedules;
     std::string err;
@@ -452,13 +454,19 @@ smk::PeerPlanes peer_planes(const smk_sim* s, int side)
 
 // piece lists of a balanced pass (pass_schedule.h): computed on the host once per (tiles, plane range, K), kept on the
 // device for the life of the simulation (a step alternates between at most a handful of ranges)
-int get_schedule(smk_sim* s, int tx, int ty, int lo, int hi, int lead, int nctas, const smk_sim::DevSchedule** out)
+int get_schedule(smk_sim* s, int tx, int ty, int lo, int hi, int lead, int nctas, const smk_sim::DevSchedule** out,
+                 int zl = INT_MIN, int zh = INT_MAX)
 {
     for (const auto& d : s->schedules)
-        if (d.tx == tx && d.ty == ty && d.lo == lo && d.hi == hi && d.lead == lead && d.nctas == nctas) { *out = &d; return SMK_OK; }
-    const sched::PassSchedule ps = sched::balance(tx, ty, lo, hi, lead, nctas);
+        if (d.tx == tx && d.ty == ty && d.lo == lo && d.hi == hi && d.lead == lead && d.nctas == nctas && d.zl == zl && d.zh == zh) {
+            *out = &d;
+            return SMK_OK;
+        }
+    sched::PassSchedule ps = sched::balance(tx, ty, lo, hi, lead, nctas);
+    int nb[2] = {0, 0};
+    if (zl != INT_MIN || zh != INT_MAX) sched::boundary_first(ps, zl, zh, nb);
     static_assert(sizeof(sched::Piece) == sizeof(int4), "pieces are uploaded as int4");
-    smk_sim::DevSchedule d{tx, ty, lo, hi, lead, nctas, nullptr, nullptr, ps.nctas(), ps.cost};
+    smk_sim::DevSchedule d{tx, ty, lo, hi, lead, nctas, zl, zh, nullptr, nullptr, ps.nctas(), ps.cost, {nb[0], nb[1]}};
     CK(s, cudaMalloc(&d.pieces, std::max<size_t>(1, ps.pieces.size()) * sizeof(int4)));
     CK(s, cudaMalloc(&d.first, ps.first.size() * sizeof(int)));
     // (blocking copies from pageable memory: first use only, i.e. during the first step)
@@ -537,8 +545,29 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
         pr.sync.first = blast ? 0 : 1;
         if (nowait) pr.sync.wait_epoch = 0; // timing experiments only (races!)
         s->pass_epoch_next = sweep0 + K;
-        kern<<<dim3((unsigned)tx, (unsigned)ty, (unsigned)nchunks), C::THREADS, C::SMEM, s->stream>>>(
-            g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk, pr, fa);
+        // balanced piece lists, boundary pieces first in every CTA (SMK_P2P_BALANCED=0: the (tile, z-chunk) grid with the
+        // boundary chunks scheduled first)
+        static const bool p2p_bal = !(getenv("SMK_P2P_BALANCED") && atoi(getenv("SMK_P2P_BALANCED")) == 0) && !blast;
+        const smk_sim::DevSchedule* ds = nullptr;
+        if (p2p_bal && s->pass_ctas >= 0) {
+            const int zl = pr.lower.u ? pr.own_lo + K : INT_MIN, zh = pr.upper.u ? pr.own_hi - K + 1 : INT_MAX;
+            int rc = get_schedule(s, tx, ty, out_lo, out_hi, sched::pass_lead(K), s->pass_ctas > 0 ? s->pass_ctas : s->num_sms, &ds, zl, zh);
+            if (rc) return rc;
+            if (s->pass_ctas == 0 && ds->cost >= sched::grid_cost(tx * ty, nz, zchunk, sched::pass_lead(K), s->num_sms)) ds = nullptr;
+        }
+        s->last_pass_ctas = ds ? ds->launch_ctas : 0;
+        if (ds) {
+            pr.sync.npieces[0] = ds->nboundary[0]; pr.sync.npieces[1] = ds->nboundary[1];
+            if (!pr.lower.u) pr.sync.wait_ctr[0] = nullptr; // (no neighbour on that side: nothing to wait for or to publish)
+            if (!pr.upper.u) pr.sync.wait_ctr[1] = nullptr;
+            auto kb = force ? smk::k_pressure_reg_bal<K, NW, true> : smk::k_pressure_reg_bal<K, NW, false>;
+            kb<<<dim3((unsigned)ds->launch_ctas), C::THREADS, C::SMEM, s->stream>>>(
+                g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, pr, fa, ds->pieces,
+                ds->first);
+        } else {
+            kern<<<dim3((unsigned)tx, (unsigned)ty, (unsigned)nchunks), C::THREADS, C::SMEM, s->stream>>>(
+                g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk, pr, fa);
+        }
     } else if (from_peers && overlap && nchunks >= 3 && zchunk >= K) {
         // The first and last z-chunk read neighbour planes; the interior chunks do not and never write planes a
         // neighbour may still be reading.  So: publish my epoch, start the interior chunks at once on the main stream, and
@@ -581,6 +610,7 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
             // default: keep the grid where it is no worse (small grids: many short chunks already fill one wave)
             if (s->pass_ctas == 0 && ds->cost >= sched::grid_cost(tx * ty, nz, zchunk, sched::pass_lead(K), s->num_sms)) ds = nullptr;
         }
+        s->last_pass_ctas = ds ? ds->launch_ctas : 0;
         if (ds) {
             auto kb = force ? smk::k_pressure_reg_bal<K, NW, true> : smk::k_pressure_reg_bal<K, NW, false>;
             kb<<<dim3((unsigned)ds->launch_ctas), C::THREADS, C::SMEM, s->stream>>>(
@@ -681,6 +711,7 @@ int stage_pressure_jacobi(smk_sim* s)
         if (rc) return rc;
         if (s->pass_ctas == 0 && ds->cost >= sched::grid_cost(xtiles * ytiles, g.nzn, zchunk, sched::JACOBI_LEAD, slots)) ds = nullptr;
     }
+    s->last_pass_ctas = ds ? ds->launch_ctas : 0;
     for (int it = 0; it < s->iterations; it++) {
         if (ds)
             smk::k_jacobi_bal<<<dim3((unsigned)ds->launch_ctas), block, 0, s->stream>>>(
@@ -1361,6 +1392,8 @@ int smk_set_pass_ctas(smk_sim* s, int nctas)
     s->pass_ctas = nctas;
     return SMK_OK;
 }
+
+int smk_last_pass_ctas(smk_sim* s) { return s ? s->last_pass_ctas : -SMK_ERR_ARG; }
 
 int smk_set_stream(smk_sim* s, void* cuda_stream)
 {

@@ -68,10 +68,13 @@ def test_virtual_slabs_bit_identical_to_single_gpu(po, smk, world, ghost, fuse, 
 
 @pytest.mark.parametrize("world,ghost,fuse,dims", [(2, 8, 4, (70, 40, 48)), (4, 4, 4, (40, 30, 64)), (3, 5, 4, (60, 37, 41)),
                                                    (2, 6, 2, (20, 18, 30))])
-def test_peer_memory_path_bit_identical_to_single_gpu(po, smk, world, ghost, fuse, dims):
+@pytest.mark.parametrize("ctas", [0, -1, 3, 148])
+def test_peer_memory_path_bit_identical_to_single_gpu(po, smk, world, ghost, fuse, dims, ctas):
     """The B200-native transport: pressure passes read the neighbours' boundary planes straight from their memory
     (epoch handshake per pass, no ghost copies), halo refreshes before advection are pulls over the mapped memory.
-    Virtual slabs in one process (pointer attach instead of CUDA IPC); every rank just runs smk_step_async."""
+    Virtual slabs in one process (pointer attach instead of CUDA IPC); every rank just runs smk_step_async.
+    ctas: schedule of a pass -- library default, the (tile, z-chunk) grid, balanced piece lists on 3 / 148 CTAs (boundary
+    pieces first, in-kernel handshake per piece)."""
     from smoke_simulation_b200 import slab
     W, H, D = dims
     iterations, steps, dt = 7, 3, 0.05
@@ -81,7 +84,7 @@ def test_peer_memory_path_bit_identical_to_single_gpu(po, smk, world, ghost, fus
     sims = []
     for r in range(world):
         s = smk.SmokeSim(W, H, D, slab=(r, world), ghost=ghost)
-        po.setup_scene(s, scene); inject(po, s, st); s.set_solver(0, iterations, fuse)
+        po.setup_scene(s, scene); inject(po, s, st); s.set_solver(0, iterations, fuse); s.set_pass_ctas(ctas)
         sims.append(s)
     slab.attach_peers_local(sims)
     # One host thread drives all slabs on one GPU: run the plan op by op and enqueue every slab's epoch signal before any
