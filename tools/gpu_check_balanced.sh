@@ -15,13 +15,11 @@ timeout 600 python bench.py > $O/bench_n1.json 2> $O/bench_n1.err; echo "rc=$?"
 stamp "bench grid (SMK_PASS_BALANCED=0)"
 SMK_PASS_BALANCED=0 timeout 300 python bench.py --no-cpu-baseline > $O/bench_n1_grid.json 2> $O/bench_n1_grid.err
 stamp "bench C3"
-timeout 300 python bench.py --workload C3 --steps 10 --no-cpu-baseline > $O/bench_c3.json 2> $O/bench_c3.err
-SMK_PASS_BALANCED=0 timeout 300 python bench.py --workload C3 --steps 10 --no-cpu-baseline > $O/bench_c3_grid.json 2> $O/bench_c3_grid.err
+timeout 300 python bench.py --workload C3 --steps 6 --no-cpu-baseline > $O/bench_c3.json 2> $O/bench_c3.err
+SMK_PASS_BALANCED=0 timeout 300 python bench.py --workload C3 --steps 6 --no-cpu-baseline > $O/bench_c3_grid.json 2> $O/bench_c3_grid.err
 stamp "bench jacobi"
 timeout 300 python bench.py --solver jacobi --no-cpu-baseline > $O/bench_jacobi.json 2> $O/bench_jacobi.err
 SMK_PASS_BALANCED=0 timeout 300 python bench.py --solver jacobi --no-cpu-baseline > $O/bench_jacobi_grid.json 2> $O/bench_jacobi_grid.err
-stamp "bench C1"
-timeout 300 python bench.py --workload C1 --no-cpu-baseline > $O/bench_c1.json 2> $O/bench_c1.err
 stamp "ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/ncu_list.log 2>&1
@@ -29,7 +27,7 @@ stamp "ncu full, one balanced pass"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pressure_reg_bal -s 20 -c 1 -f -o $O/prof_bal \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $O/ncu_full.log 2>&1
 stamp "done"
-for f in bench_n1 bench_n1_grid bench_c3 bench_c3_grid bench_jacobi bench_jacobi_grid bench_c1; do
+for f in bench_n1 bench_n1_grid bench_c3 bench_c3_grid bench_jacobi bench_jacobi_grid; do
   python - "$O/$f.json" <<'PY'
 import json,sys
 try:
