@@ -124,9 +124,9 @@ float* smk_buoyancy_ptr(smk_sim* s);
  * fuse = number of half-sweeps fused per kernel launch (temporal blocking); 0 = library default,
  * 1 = one launch per half-sweep.  Results are identical for every fuse value. */
 int smk_set_solver(smk_sim* s, int variant, int iterations, int fuse);
-/* scheduling of the fused pressure passes (no effect on results): nctas > 0 = run every pass as that many CTAs with
- * balanced piece lists (csrc/pass_schedule.h); 0 = default (one CTA per SM, or the (tile, z-chunk) grid where that is
- * no slower); -1 = always the (tile, z-chunk) grid. */
+/* scheduling of the fused pressure passes (no effect on results): 0 = default, a (tile, z-chunk) grid of CTAs;
+ * nctas > 0 = that many CTAs working through balanced piece lists (csrc/pass_schedule.h; an experiment kept for
+ * ablation: measured no faster). */
 int smk_set_pass_ctas(smk_sim* s, int nctas);
 /* CTAs of the most recent pressure pass if it ran on balanced piece lists, 0 if it ran as a (tile, z-chunk) grid */
 int smk_last_pass_ctas(smk_sim* s);

@@ -387,7 +387,7 @@ k_pressure_reg(GridP g, const float* __restrict__ ui, const float* __restrict__ 
     }
 }
 
-// Balanced schedule: ONE CTA per SM, each working through its own list of pieces -- pieces[first[b] .. first[b+1]) =
+// Balanced schedule (opt-in experiment, see pass_schedule.h): ONE CTA per SM, each working through its own list of pieces -- pieces[first[b] .. first[b+1]) =
 // (tile x, tile y, zo0, zo1) -- which the host cuts so that every CTA marches the same number of z-steps (lead-in planes
 // included).  A (tile, z-chunk) grid quantises into waves (275 CTAs on 148 SMs = 2 rounds of 58 steps at 256^3); equal
 // shares need 104.

@@ -6,6 +6,9 @@
 // scheduling decision:
 //   * a (tile, z-chunk) grid, one piece per CTA (k_pressure_reg): simple, but CTAs quantise into waves over the SMs;
 //   * this header: `nctas` CTAs (one per SM), each with a LIST of pieces of equal total cost (k_pressure_reg_bal).
+// STATUS: an experiment kept for ablation (smk_set_pass_ctas / SMK_PASS_CTAS), not the default.  On the B200 the equal
+// shares (104 instead of 116 z-steps at 256^3) buy nothing: neighbouring tiles are no longer at the same z at the same
+// time, their halo re-reads miss L2 and DRAM reads double (profiles/r1_balanced_schedule.txt).
 // The reference has no counterpart (one thread per cell, cu:795-801); the tests check coverage and balance on the CPU
 // through the host-only entry point smk_pass_schedule.
 #pragma once

@@ -92,7 +92,7 @@ struct smk_sim {
     bool mask_dirty = true; // the mask / stencil codes on the device do not reflect the current obstacle list yet
     int iterations = 30; // cu:797
     int fuse = 0;
-    int pass_ctas = 0;   // smk_set_pass_ctas
+    int pass_ctas = getenv("SMK_PASS_CTAS") ? atoi(getenv("SMK_PASS_CTAS")) : 0; // smk_set_pass_ctas (0: chunk grid)
     int last_pass_ctas = 0; // CTAs of the last balanced pass launch (0: it was a (tile, z-chunk) grid)
 
     // slab decomposition (single GPU: owns everything, no ghosts); schedule and validity tracking in slab_plan.h
@@ -469,9 +469,12 @@ int get_schedule(smk_sim* s, int tx, int ty, int lo, int hi, int lead, int nctas
     smk_sim::DevSchedule d{tx, ty, lo, hi, lead, nctas, zl, zh, nullptr, nullptr, ps.nctas(), ps.cost, {nb[0], nb[1]}};
     CK(s, cudaMalloc(&d.pieces, std::max<size_t>(1, ps.pieces.size()) * sizeof(int4)));
     CK(s, cudaMalloc(&d.first, ps.first.size() * sizeof(int)));
-    // (blocking copies from pageable memory: first use only, i.e. during the first step)
-    if (!ps.pieces.empty()) CK(s, cudaMemcpy(d.pieces, ps.pieces.data(), ps.pieces.size() * sizeof(int4), cudaMemcpyHostToDevice));
-    CK(s, cudaMemcpy(d.first, ps.first.data(), ps.first.size() * sizeof(int), cudaMemcpyHostToDevice));
+    // Uploaded IN STREAM ORDER (first use only): a plain cudaMemcpy from pageable memory may return before its DMA has
+    // landed, and the step's stream is not ordered behind the default stream.  cudaMemcpyAsync stages pageable
+    // sources before it returns, so the host vectors may go out of scope.
+    if (!ps.pieces.empty())
+        CK(s, cudaMemcpyAsync(d.pieces, ps.pieces.data(), ps.pieces.size() * sizeof(int4), cudaMemcpyHostToDevice, s->stream));
+    CK(s, cudaMemcpyAsync(d.first, ps.first.data(), ps.first.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
     s->schedules.push_back(d);
     *out = &s->schedules.back();
     return SMK_OK;
@@ -545,15 +548,12 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
         pr.sync.first = blast ? 0 : 1;
         if (nowait) pr.sync.wait_epoch = 0; // timing experiments only (races!)
         s->pass_epoch_next = sweep0 + K;
-        // balanced piece lists, boundary pieces first in every CTA (SMK_P2P_BALANCED=0: the (tile, z-chunk) grid with the
-        // boundary chunks scheduled first)
-        static const bool p2p_bal = !(getenv("SMK_P2P_BALANCED") && atoi(getenv("SMK_P2P_BALANCED")) == 0) && !blast;
+        // opt-in (smk_set_pass_ctas): balanced piece lists, boundary pieces first in every CTA
         const smk_sim::DevSchedule* ds = nullptr;
-        if (p2p_bal && s->pass_ctas >= 0) {
+        if (s->pass_ctas > 0) {
             const int zl = pr.lower.u ? pr.own_lo + K : INT_MIN, zh = pr.upper.u ? pr.own_hi - K + 1 : INT_MAX;
-            int rc = get_schedule(s, tx, ty, out_lo, out_hi, sched::pass_lead(K), s->pass_ctas > 0 ? s->pass_ctas : s->num_sms, &ds, zl, zh);
+            int rc = get_schedule(s, tx, ty, out_lo, out_hi, sched::pass_lead(K), s->pass_ctas, &ds, zl, zh);
             if (rc) return rc;
-            if (s->pass_ctas == 0 && ds->cost >= sched::grid_cost(tx * ty, nz, zchunk, sched::pass_lead(K), s->num_sms)) ds = nullptr;
         }
         s->last_pass_ctas = ds ? ds->launch_ctas : 0;
         if (ds) {
@@ -599,16 +599,15 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
             int rc = peer_sync(s);
             if (rc) return rc;
         }
-        // All planes this pass reads are local (single GPU, ghost planes, or handshake done above): no CTA waits for
-        // another, so the pass runs as one CTA per SM with piece lists of equal cost instead of a (tile, z-chunk) grid
-        // that quantises into waves.  SMK_PASS_BALANCED=0 keeps the grid (ablation).
-        static const bool balanced = !(getenv("SMK_PASS_BALANCED") && atoi(getenv("SMK_PASS_BALANCED")) == 0);
+        // Default: the (tile, z-chunk) grid.  Opt-in (smk_set_pass_ctas / SMK_PASS_CTAS=n): n CTAs working through piece
+        // lists of equal cost (pass_schedule.h).  Measured at 256^3 / 512^3 with one CTA per SM: 104 instead of 116 z-steps
+        // on the busiest SM, but neighbouring tiles are no longer at the same z at the same time, their halo re-reads
+        // miss L2 (hit rate 4 % instead of 31 %, DRAM reads 506 MB instead of 250 MB per pass) and the pass is no
+        // faster (256^3) or 15 % slower (512^3): profiles/r1_balanced_schedule.txt.
         const smk_sim::DevSchedule* ds = nullptr;
-        if (balanced && nz > 0 && s->pass_ctas >= 0) {
-            int rc = get_schedule(s, tx, ty, out_lo, out_hi, sched::pass_lead(K), s->pass_ctas > 0 ? s->pass_ctas : s->num_sms, &ds);
+        if (s->pass_ctas > 0 && nz > 0) {
+            int rc = get_schedule(s, tx, ty, out_lo, out_hi, sched::pass_lead(K), s->pass_ctas, &ds);
             if (rc) return rc;
-            // default: keep the grid where it is no worse (small grids: many short chunks already fill one wave)
-            if (s->pass_ctas == 0 && ds->cost >= sched::grid_cost(tx * ty, nz, zchunk, sched::pass_lead(K), s->num_sms)) ds = nullptr;
         }
         s->last_pass_ctas = ds ? ds->launch_ctas : 0;
         if (ds) {
@@ -702,14 +701,12 @@ int stage_pressure_jacobi(smk_sim* s)
     const int zchunk = (g.nzn + nchunk - 1) / nchunk;
     nchunk = (g.nzn + zchunk - 1) / zchunk;
     dim3 block(smk::JTHREADS), grid(xtiles, ytiles, nchunk);
-    // balanced piece lists (pass_schedule.h) over the CTAs that fit the GPU at once, unless the grid is no worse
-    static const bool balanced = !(getenv("SMK_PASS_BALANCED") && atoi(getenv("SMK_PASS_BALANCED")) == 0);
+    // opt-in (smk_set_pass_ctas): balanced piece lists (pass_schedule.h); measured slower than the grid for the same
+    // reason as the RBGS passes (neighbouring tiles out of step -> their shared rows miss L2)
     const smk_sim::DevSchedule* ds = nullptr;
-    if (balanced && s->pass_ctas >= 0) {
-        const int slots = 2 * s->num_sms;
-        int rc = get_schedule(s, xtiles, ytiles, 0, g.nzn, sched::JACOBI_LEAD, s->pass_ctas > 0 ? s->pass_ctas : slots, &ds);
+    if (s->pass_ctas > 0) {
+        int rc = get_schedule(s, xtiles, ytiles, 0, g.nzn, sched::JACOBI_LEAD, s->pass_ctas, &ds);
         if (rc) return rc;
-        if (s->pass_ctas == 0 && ds->cost >= sched::grid_cost(xtiles * ytiles, g.nzn, zchunk, sched::JACOBI_LEAD, slots)) ds = nullptr;
     }
     s->last_pass_ctas = ds ? ds->launch_ctas : 0;
     for (int it = 0; it < s->iterations; it++) {
@@ -1388,7 +1385,7 @@ int smk_set_solver(smk_sim* s, int variant, int iterations, int fuse)
 
 int smk_set_pass_ctas(smk_sim* s, int nctas)
 {
-    if (!s || nctas < -1) return SMK_ERR_ARG;
+    if (!s || nctas < 0) return SMK_ERR_ARG;
     s->pass_ctas = nctas;
     return SMK_OK;
 }

@@ -1,6 +1,6 @@
 """Host-only checks of the balanced piece lists of a fused pressure pass (csrc/pass_schedule.h through the C ABI
 smk_pass_schedule): every (tile, output plane) is covered exactly once, no CTA exceeds the reported cost, the shares
-are balanced, and the cost beats the (tile, z-chunk) grid on the bench workloads.  No GPU needed."""
+are balanced, and the z-step counts quoted in DESIGN.md.  No GPU needed."""
 import numpy as np
 import pytest
 
@@ -43,8 +43,10 @@ def test_pieces_cover_every_plane_once_and_are_balanced(smk, W, H, lo, hi, K, nc
         assert min(costs) >= 0.5 * s["cost"]
 
 
-def test_balanced_beats_the_chunk_grid_on_the_bench_workloads(smk):
-    """z-steps of the busiest SM: (tile, z-chunk) grid in waves vs equal shares."""
+def test_balanced_needs_fewer_z_steps_than_the_chunk_grid(smk):
+    """z-steps of the busiest SM: (tile, z-chunk) grid in waves vs equal shares.  (Fewer steps did NOT make the pass faster
+    on the B200 -- neighbouring tiles fall out of step and their halo re-reads miss L2, DESIGN.md section 4 -- which is why
+    the grid stays the default; this only pins the step counts quoted there: 104 vs 116 at 256^3, 778 vs 789 at 512^3.)"""
     from smoke_simulation_b200 import slab as sl
 
     def grid_cost(tiles, nz, K, sms=148):
@@ -61,7 +63,11 @@ def test_balanced_beats_the_chunk_grid_on_the_bench_workloads(smk):
         s = sl.pass_schedule(W, W, 0, nz, 4, 148)
         tx, ty = s["tiles"]
         gc = grid_cost(tx * ty, nz, 4)
-        if gain is None:   # 80^3: many short chunks already fill one wave; the launcher keeps the grid when it is no worse
+        if W == 256:
+            assert (s["cost"], gc) == (104, 116)
+        if W == 512:
+            assert (s["cost"], gc) == (778, 789)
+        if gain is None:   # 80^3: many short chunks already fill one wave
             assert s["cost"] <= gc + 2
         else:
             assert s["cost"] <= gain * gc, (W, s["cost"], gc)
