@@ -41,9 +41,13 @@ struct RegCfg {
 
 // exact q = d / acc for the neighbour counts 1..6 (see pressure_p_fast); returns true if any lane needs the
 // IEEE fallback (denormal-range d with acc = 6 is the only inexact case)
+// -OVER_RELAXATION as a double (cu:38, 384) in constant memory: DMUL takes it as a constant-bank operand instead of two
+// register moves per sweep
+__constant__ double c_m19 = -1.9;
+#define M19 c_m19
 __device__ __forceinline__ float2 p_pair_from_q(float2 q)
 {
-    return make_float2(__double2float_rn(__dmul_rn((double)q.x, -1.9)), __double2float_rn(__dmul_rn((double)q.y, -1.9)));
+    return make_float2(__double2float_rn(__dmul_rn((double)q.x, M19)), __double2float_rn(__dmul_rn((double)q.y, M19)));
 }
 
 // One sweep phase of one lane on ring position J (plane t-J): two same-colour cells of the lane's quad.
@@ -83,11 +87,11 @@ __device__ __forceinline__ void reg_update(float2& ue, float2& uo, float2& we, f
         float2 P = p_pair_from_q(q);
         // the correction sequence is exact for every |d| >= 2^-125 (exhaustive check); below that (and d != 0)
         // a tie on the denormal grid can round the wrong way -> IEEE division for those lanes
-        const unsigned ax = __float_as_uint(d.x) & 0x7fffffffu, ay = __float_as_uint(d.y) & 0x7fffffffu;
-        const bool sx = (ax - 1u < 0x00ffffffu) && (actm & 0x40u), sy = (ay - 1u < 0x00ffffffu) && (actm & 0x400000u);
-        if (__any_sync(0xffffffffu, sx || sy)) {
-            if (sx) P.x = __double2float_rn(__dmul_rn((double)div6_tiny(d.x), -1.9));
-            if (sy) P.y = __double2float_rn(__dmul_rn((double)div6_tiny(d.y), -1.9));
+        // (tested on every cell, active or not: a cell that is not updated gets P = 0 below anyway)
+        const unsigned ax = (__float_as_uint(d.x) & 0x7fffffffu) - 1u, ay = (__float_as_uint(d.y) & 0x7fffffffu) - 1u;
+        if (__any_sync(0xffffffffu, min(ax, ay) < 0x00ffffffu)) {
+            if (ax < 0x00ffffffu) P.x = __double2float_rn(__dmul_rn((double)div6_tiny(d.x), M19));
+            if (ay < 0x00ffffffu) P.y = __double2float_rn(__dmul_rn((double)div6_tiny(d.y), M19));
         }
         if (!(actm & 0x40u)) P.x = 0.f;      // cells that are not updated: old -/+ 0 = old
         if (!(actm & 0x400000u)) P.y = 0.f;
@@ -108,8 +112,8 @@ __device__ __forceinline__ void reg_update(float2& ue, float2& uo, float2& we, f
         const unsigned ax = __float_as_uint(d.x) & 0x7fffffffu, ay = __float_as_uint(d.y) & 0x7fffffffu;
         const bool sx = nA == 6 && (ax - 1u < 0x00ffffffu), sy = nB == 6 && (ay - 1u < 0x00ffffffu);
         if (__any_sync(0xffffffffu, sx || sy)) { // only acc = 6 can miss (exhaustive check, see pressure_p_fast)
-            if (sx) P.x = __double2float_rn(__dmul_rn((double)div6_tiny(d.x), -1.9));
-            if (sy) P.y = __double2float_rn(__dmul_rn((double)div6_tiny(d.y), -1.9));
+            if (sx) P.x = __double2float_rn(__dmul_rn((double)div6_tiny(d.x), M19));
+            if (sy) P.y = __double2float_rn(__dmul_rn((double)div6_tiny(d.y), M19));
         }
         // old - 0 and old + 0 return old (up to the sign of a zero): a masked face keeps its value
         U0 = __ffma2_rn(make_float2((cA & CODE_SX0) ? P.x : 0.f, (cB & CODE_SX0) ? P.y : 0.f), M1, U0);
@@ -205,12 +209,12 @@ __device__ __forceinline__ void reg_pass_piece(const GridP& g, const float* __re
     const int h = lane & 15;                                 // quad index inside the row
     // This half-warp's row.  Trapezoid halo: after sweep s the face rows [s, LY-1-s] of the tile are right, so sweep j is
     // only needed on the cell rows [j-1, LY-1-j]: row r needs the sweeps j <= min(r+1, LY-1-r).  Both rows of a warp must
-    // share the x parity of the active colour, so the shallow rows are paired with each other -- (0,30) (1,29) (2,28),
+    // share the x parity of the active colour, so the shallow rows are paired with each other -- (0,LY-2) (1,LY-3) (2,LY-4),
     // needing 1, 2, 3 sweeps -- and those warps skip the sweeps their rows do not need (6 of the 64 warp-sweeps of a
-    // step); (3,31) and the remaining pairs (w, w+12) run all K.  Other configurations keep the plain (w, w+NW) pairing.
-    constexpr bool SKIP = (K == 4 && NW == 16);
+    // step at LY = 32); (3,LY-1) and the remaining pairs (w, w+(LY-8)/2) run all K.  K = 2 keeps the plain (w, w+NW) pairing.
+    constexpr bool SKIP = (K == 4 && NW >= 8 && NW % 4 == 0); // ((LY - 8) / 2 even: the pairs (w, w + (LY-8)/2) share the parity)
     const int hb = lane >> 4;
-    const int yl = !SKIP ? wid + hb * NW : wid >= 4 ? wid + hb * 12 : hb == 0 ? wid : wid == 3 ? 31 : 30 - wid;
+    const int yl = !SKIP ? wid + hb * NW : wid >= 4 ? wid + hb * ((LY - 8) / 2) : hb == 0 ? wid : wid == 3 ? LY - 1 : LY - 2 - wid;
     const int jmax = (SKIP && wid < 3) ? wid + 1 : K; // deepest sweep this warp's rows need (warp uniform)
     const int x0 = bx * C::OX - C::HX;
     const int y0 = by * C::OY - K;

@@ -653,6 +653,7 @@ int launch_fused_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_
     if (K == 2 && cfg == 0) return launch_reg_pass<2, 16>(s, sweep0, out_lo, out_hi, false);
     if (K == 2 && cfg == 20) return launch_reg_pass<2, 20>(s, sweep0, out_lo, out_hi, false);
     if (K == 4 && cfg == 24) return launch_reg_pass<4, 24>(s, sweep0, out_lo, out_hi, from_peers);
+    if (K == 4 && cfg == 20) return launch_reg_pass<4, 20>(s, sweep0, out_lo, out_hi, from_peers);
     if (K == 4 && cfg == 12) return launch_reg_pass<4, 12>(s, sweep0, out_lo, out_hi, from_peers);
     switch (cfg) {
     case 163: return launch_fused_pass_cfg<K, 16, 3>(s, sweep0);
