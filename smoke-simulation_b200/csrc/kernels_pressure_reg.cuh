@@ -137,6 +137,8 @@ __device__ __forceinline__ void reg_update(float2& ue, float2& uo, float2& we, f
 // Where the planes outside the slab's OWNED range come from in a multi-GPU run: directly from the neighbour's memory
 // (peer-mapped over NVLink), i.e. the halo transfer is fused into the pressure pass plane by plane -- no ghost copy,
 // no separate exchange.  u == nullptr: no neighbour on that side / single GPU (planes come from the local arrays).
+// All four pointers are VIRTUAL PLANE-0 bases (pointer to the first stored plane minus zlo planes, set by the host), so
+// that a lane addresses plane z of any source with the same running offset.
 struct PeerPlanes {
     const float* u; const float* v; const float* w; // the neighbour's current "in" buffers
     int zlo;                                         // global index of the neighbour's first stored plane
@@ -170,6 +172,7 @@ struct PassRange {
     int own_lo, own_hi;  // node planes owned by this slab (inclusive); outside them a peer is the source if present
     int chunk_first, chunk_step; // z-chunk of block z = chunk_first + blockIdx.z * chunk_step (boundary / interior launches)
     PeerPlanes lower, upper;
+    PeerPlanes local;    // this slab's own input set and density, as plane-0 bases like the neighbours'
     PassSync sync;
 };
 
@@ -245,27 +248,31 @@ __device__ __forceinline__ void reg_pass_piece(const GridP& g, const float* __re
     unsigned pc;
     const bool dok = FORCE && xg >= 0 && xg <= g.W - 4 && yg >= 0 && yg < g.H; // W % 4 == 0 (host checks)
     const int doff = dok ? xg + yg * g.W : 0;
-    auto prefetch = [&](int z) {
-        // source of plane z: the local arrays, or a neighbour's memory for planes outside the owned range
-        const float *su = ui, *sv_ = vi, *sw = wi, *sd = fa.smoke;
-        int szlo = g.zlo;
+    // Running element offsets of this lane's quad in plane z relative to the (virtual) plane 0 of a source: one 64-bit
+    // add per step instead of a 64-bit multiply per pointer.  The source -- the local arrays, or a neighbour's memory for
+    // planes outside the owned range -- only selects the warp-uniform base pointers (kernel parameters).
+    long long bn = (long long)t0 * g.nplane + noff, bk = (long long)(t0 - g.zlo) * g.kplane + koff, bd = (long long)t0 * g.cplane + doff;
+    auto prefetch = [&](int z) { // called for z = t0, t0 + 1, ...: every plane exactly once, in order
+        const float *su = pr.local.u, *sv_ = pr.local.v, *sw = pr.local.w, *sd = pr.local.smoke;
         bool zn = z >= g.zlo && z < g.zlo + g.nzn;
-        if (z < pr.own_lo && pr.lower.u) { su = pr.lower.u; sv_ = pr.lower.v; sw = pr.lower.w; sd = pr.lower.smoke; szlo = pr.lower.zlo; zn = z >= szlo; }
-        else if (z > pr.own_hi && pr.upper.u) { su = pr.upper.u; sv_ = pr.upper.v; sw = pr.upper.w; sd = pr.upper.smoke; szlo = pr.upper.zlo; zn = z <= g.D; }
+        if (z < pr.own_lo && pr.lower.u) { su = pr.lower.u; sv_ = pr.lower.v; sw = pr.lower.w; sd = pr.lower.smoke; zn = z >= pr.lower.zlo; }
+        else if (z > pr.own_hi && pr.upper.u) { su = pr.upper.u; sv_ = pr.upper.v; sw = pr.upper.w; sd = pr.upper.smoke; zn = z <= g.D; }
         const bool zc = z >= g.zlo && z < g.zlo + g.nzc;
         if (FORCE) {
             pd = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (zn && zc && dok) pd = __ldg(reinterpret_cast<const float4*>(sd + (long long)(z - szlo) * g.cplane + doff));
+            if (zn && zc && dok) pd = __ldg(reinterpret_cast<const float4*>(sd + bd));
+            bd += g.cplane;
         }
         pu = pv = pw = make_float4(0.f, 0.f, 0.f, 0.f);
         pc = 0;
         if (zn && nok) {
-            const long long n = (long long)(z - szlo) * g.nplane + noff;
-            pu = __ldg(reinterpret_cast<const float4*>(su + n));
-            pv = __ldg(reinterpret_cast<const float4*>(sv_ + n));
-            pw = __ldg(reinterpret_cast<const float4*>(sw + n));
+            pu = __ldg(reinterpret_cast<const float4*>(su + bn));
+            pv = __ldg(reinterpret_cast<const float4*>(sv_ + bn));
+            pw = __ldg(reinterpret_cast<const float4*>(sw + bn));
         }
-        if (zc && kok) pc = __ldg(reinterpret_cast<const unsigned*>(code + (long long)(z - g.zlo) * g.kplane + koff));
+        if (zc && kok) pc = __ldg(reinterpret_cast<const unsigned*>(code + bk));
+        bn += g.nplane;
+        bk += g.kplane;
     };
 
     prefetch(t0);

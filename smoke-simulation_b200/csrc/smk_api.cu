@@ -438,17 +438,24 @@ int peer_sync(smk_sim* s)
     return peer_wait(s, s->stream);
 }
 
+// pointer to the (virtual) plane 0 of a field whose first stored plane is zlo; never dereferenced outside the stored planes
+const float* plane0(const float* first_stored, long long plane, int zlo)
+{
+    return reinterpret_cast<const float*>(reinterpret_cast<uintptr_t>(first_stored) - (uintptr_t)((long long)zlo * plane * 4));
+}
+
 smk::PeerPlanes peer_planes(const smk_sim* s, int side)
 {
     smk::PeerPlanes p{nullptr, nullptr, nullptr, 0, nullptr};
     const auto& pe = s->peer[side];
     if (!pe.arena) return p;
     const int id = s->vel_id[s->now]; // same physical buffer on every rank (identical swap history)
-    p.u = reinterpret_cast<const float*>(pe.arena + pe.lay.u[id]);
-    p.v = reinterpret_cast<const float*>(pe.arena + pe.lay.v[id]);
-    p.w = reinterpret_cast<const float*>(pe.arena + pe.lay.w[id]);
     p.zlo = pe.geom.zlo;
-    p.smoke = reinterpret_cast<const float*>(pe.arena + pe.lay.smoke[s->now]);
+    // virtual plane-0 bases (kernels_pressure_reg.cuh): plane strides are the same on every slab (same W, H)
+    p.u = plane0(reinterpret_cast<const float*>(pe.arena + pe.lay.u[id]), s->g.nplane, p.zlo);
+    p.v = plane0(reinterpret_cast<const float*>(pe.arena + pe.lay.v[id]), s->g.nplane, p.zlo);
+    p.w = plane0(reinterpret_cast<const float*>(pe.arena + pe.lay.w[id]), s->g.nplane, p.zlo);
+    p.smoke = plane0(reinterpret_cast<const float*>(pe.arena + pe.lay.smoke[s->now]), s->g.cplane, p.zlo);
     return p;
 }
 
@@ -505,6 +512,8 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
     pr.out_lo = out_lo; pr.out_hi = out_hi;
     pr.own_lo = g.zlo; pr.own_hi = g.zlo + g.nzn - 1; // default: everything stored counts as "own" (local source)
     pr.chunk_first = 0; pr.chunk_step = 1;
+    pr.local = smk::PeerPlanes{plane0(s->u[s->now], g.nplane, g.zlo), plane0(s->v[s->now], g.nplane, g.zlo),
+                               plane0(s->w[s->now], g.nplane, g.zlo), g.zlo, plane0(s->smoke[s->now], g.cplane, g.zlo)};
     const int nz = out_hi - out_lo;
     const int tx = (g.W + 1 + C::OX - 1) / C::OX, ty = (g.SY + C::OY - 1) / C::OY;
     const int zchunk = pick_zchunk(s, tx * ty, K, nz);
