@@ -275,6 +275,9 @@ __device__ __forceinline__ void reg_pass_piece(const GridP& g, const float* __re
         bk += g.kplane;
     };
 
+    // running offset of this lane's quad in the OUTPUT plane t-K (u, w; v is written one plane behind)
+    long long bo = (long long)(t0 - K - g.zlo) * g.nplane + noff;
+    float* const vo_below = vo - g.nplane;
     prefetch(t0);
     int slot_t = 0; // shared-memory slot of plane t (the same slot held plane t-K-1)
     for (int t = t0; t <= t1 + 1; t++) {
@@ -285,7 +288,7 @@ __device__ __forceinline__ void reg_pass_piece(const GridP& g, const float* __re
             if (s2 >= zo0 && s2 < zo1 && sok) {
                 const float* p = sv + slot_t * PLS + vrow;
                 const float2 ve = *reinterpret_cast<const float2*>(p), vo2 = *reinterpret_cast<const float2*>(p + HO);
-                *reinterpret_cast<float4*>(vo + (long long)(s2 - g.zlo) * g.nplane + noff) = make_float4(ve.x, vo2.x, ve.y, vo2.y);
+                *reinterpret_cast<float4*>(vo_below + bo) = make_float4(ve.x, vo2.x, ve.y, vo2.y);
             }
         }
         if (t > t1) break;
@@ -333,10 +336,10 @@ __device__ __forceinline__ void reg_pass_piece(const GridP& g, const float* __re
         {
             const int s = t - K;
             if (s >= zo0 && s < zo1 && sok) {
-                const long long n = (long long)(s - g.zlo) * g.nplane + noff;
-                *reinterpret_cast<float4*>(uo + n) = make_float4(UE[K].x, UO[K].x, UE[K].y, UO[K].y);
-                *reinterpret_cast<float4*>(wo + n) = make_float4(WE[K].x, WO[K].x, WE[K].y, WO[K].y);
+                *reinterpret_cast<float4*>(uo + bo) = make_float4(UE[K].x, UO[K].x, UE[K].y, UO[K].y);
+                *reinterpret_cast<float4*>(wo + bo) = make_float4(WE[K].x, WO[K].x, WE[K].y, WO[K].y);
             }
+            bo += g.nplane;
         }
         // (e) shift the register ring
 #pragma unroll
