@@ -287,6 +287,33 @@ def test_c2_256_one_tick_property_checks(po, smk):
     a.close()
 
 
+def test_c3_512_two_ticks_identical_to_reference_gpu_build(po, smk):
+    """BASELINE configs[2] at full size (512^3, source + solid sphere): two ticks of the default schedule (fused passes,
+    TMA advection, forcing riding on the first pass) against the reference step itself built for sm_100a -- mask
+    bit-exact, every field identical, field by field to bound host memory -- plus size-independent properties."""
+    if not po.have_ref_gpu():
+        pytest.skip("oracle/_ref/libref_gpu.so not in the snapshot")
+    sc = po.SCENES["C3"]
+    a = smk.SmokeSim(*sc[:3]); po.setup_scene(a, sc)
+    r = po.RefGPU(*sc[:3]); po.setup_scene(r, sc)
+    try:
+        for t in range(2):
+            a.step(po.tick_dt(t)); r.step(po.tick_dt(t))
+        ma = a.get_field(po.MASK)
+        assert np.array_equal(ma, r.get_field(po.MASK))
+        assert int((ma == 0).sum()) > 512 * 512            # the floor plane and the sphere
+        for f in (po.SMOKE, po.U, po.V, po.W):
+            for which in (po.NOW, po.PAST):
+                x, y = a.get_field(f, which), r.get_field(f, which)
+                assert np.array_equal(x, y), (f, which, rel_err(x, y))
+                if f == po.SMOKE:
+                    assert x.min() >= 0.0 and x.max() <= 1.0 + 1e-6
+                del x, y
+        assert a.max_divergence() < 1.0
+    finally:
+        r.close(); a.close()
+
+
 @pytest.mark.parametrize("fuse", [1, 2, 4])
 @pytest.mark.parametrize("dims", [(20, 18, 16), (120, 50, 40), (57, 41, 9), (130, 100, 70)])
 def test_fused_pressure_passes_identical(po, smk, dims, fuse):
