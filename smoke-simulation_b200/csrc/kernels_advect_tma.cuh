@@ -61,13 +61,15 @@ struct Staged {
     const float* base; // [NSLOT][SLOT_FLOATS]
     int x0, y0;        // global coordinates of box element (0,0)
     int zc;            // plane being computed: planes zc-HALO .. zc+HALO are resident
+    int sb;            // ring slot of plane zc-HALO
     __device__ __forceinline__ bool holds(int xa, int xb, int ya, int yb, int za, int zb) const
     {
         return xa >= x0 && xb < x0 + AdvTma::BX && ya >= y0 && yb < y0 + AdvTma::BY && za >= zc - AdvTma::HALO && zb <= zc + AdvTma::HALO;
     }
     __device__ __forceinline__ const float* row(int y, int z) const
     {
-        const int slot = (z + 4 * AdvTma::NSLOT) % AdvTma::NSLOT;
+        int slot = sb + (z - zc + AdvTma::HALO);   // z in [zc-HALO, zc+HALO] (holds()): one conditional wrap, no modulo
+        slot -= slot >= AdvTma::NSLOT ? AdvTma::NSLOT : 0;
         return base + slot * AdvTma::SLOT_FLOATS + (y - y0) * AdvTma::BX - x0;
     }
     __device__ __forceinline__ float at(int x, int y, int z) const { return row(y, z)[x]; }
@@ -147,7 +149,8 @@ k_advect_velocity_tma(GridP g, const __grid_constant__ CUtensorMap mu, const __g
             const bool doV = (cd & CODE_SELF) && (cd & CODE_SY0) && x < g.W - 1 && z < g.D - 1;
             const bool doW = (cd & CODE_SELF) && (cd & CODE_SZ0) && x < g.W - 1 && y < g.H - 1;
             if (doU || doV || doW) {
-                const Staged U{su, bx0, by0, z}, V{sv, bx0, by0, z}, Wf{sw, bx0, by0, z};
+                const int sb = (z - A::HALO + 4 * A::NSLOT) % A::NSLOT;
+                const Staged U{su, bx0, by0, z, sb}, V{sv, bx0, by0, z, sb}, Wf{sw, bx0, by0, z, sb};
                 const long long n = node_index(g, x, y, z);
                 // 8-point face sums in the reference's order (avgU/avgV/avgW cu:409-447), then *0.125
                 float au = 0.f, av = 0.f, aw = 0.f;

@@ -353,6 +353,27 @@ __device__ __forceinline__ float sample_global(const float* __restrict__ f, long
     return tri_combine(t, r00[t.x0], r00[t.x1], r10[t.x0], r10[t.x1], r01[t.x0], r01[t.x1], r11[t.x0], r11[t.x1]);
 }
 
+// The same sample with 32-bit element indices (fields of fewer than 2^31 stored elements -- every configuration of
+// SURVEY 8(d); the host checks): one 32-bit multiply-add per row and one address per corner instead of 64-bit
+// arithmetic throughout.  sy, sz = row and plane stride in elements.
+__device__ __forceinline__ float sample_global32(const float* __restrict__ f, int sy, int sz, int zlo,
+                                                 float px, float py, float pz, float dx, float dy, float dz,
+                                                 float bx, float by, float bz, int2 zv, int* __restrict__ flag)
+{
+    Tri t;
+    tri_axis(px, dx, bx, t.x0, t.x1, t.xw0, t.xw1);
+    tri_axis(py, dy, by, t.y0, t.y1, t.yw0, t.yw1);
+    tri_axis(pz, dz, bz, t.z0, t.z1, t.zw0, t.zw1);
+    if (t.z0 < zv.x || t.z1 > zv.y) { // slab runs only; clamp so the load itself stays inside the stored planes
+        *flag = 1;
+        t.z0 = max(zv.x, min(zv.y, t.z0)); t.z1 = max(zv.x, min(zv.y, t.z1));
+    }
+    const int r0 = (t.z0 - zlo) * sz, r1 = (t.z1 - zlo) * sz, q0 = t.y0 * sy, q1 = t.y1 * sy;
+    const int r00 = r0 + q0, r10 = r0 + q1, r01 = r1 + q0, r11 = r1 + q1;
+    return tri_combine(t, f[r00 + t.x0], f[r00 + t.x1], f[r10 + t.x0], f[r10 + t.x1], f[r01 + t.x0], f[r01 + t.x1],
+                       f[r11 + t.x0], f[r11 + t.x1]);
+}
+
 // 8-point face sums (avgU/avgV/avgW cu:409-447) in source order, then *0.125 (= /8 exactly).
 // f points at node (x,y,z); P = row pitch, S = plane stride.
 __device__ __forceinline__ float avg_u8(const float* __restrict__ f, long long P, long long S)
@@ -472,6 +493,29 @@ __global__ void __launch_bounds__(256) k_advect_smoke(GridP g, const float* __re
     const float pz = __double2float_rn(__dadd_rn(__dadd_rn((double)z, 0.5), (double)mw));
     const float bx = (float)(unsigned)(g.W - 1), by = (float)(unsigned)(g.H - 1), bz = (float)(unsigned)(g.D - 1);
     s1[c] = sample_global(s0, g.W, g.cplane, g.zlo, px, py, pz, .5f, .5f, .5f, bx, by, bz, zv, flag);
+}
+
+// The same kernel with 32-bit element indices (host: every stored field has fewer than 2^31 elements).
+__global__ void __launch_bounds__(256) k_advect_smoke32(GridP g, const float* __restrict__ s0, float* __restrict__ s1,
+                                                        const float* __restrict__ u, const float* __restrict__ v,
+                                                        const float* __restrict__ w, const unsigned char* __restrict__ code,
+                                                        float dt, int za, int zb, int2 zv, int* __restrict__ flag)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int z = za + blockIdx.z * blockDim.z + threadIdx.z;
+    if (x < 1 || y < 1 || z < 1 || x >= g.W - 1 || y >= g.H - 1 || z >= zb || z >= g.D - 1) return;
+    const int zr = z - g.zlo, cpl = (int)g.cplane, npl = (int)g.nplane;
+    if (!(code[x + y * g.PC + zr * (int)g.kplane] & CODE_SELF)) return;
+    const int n = x + y * g.P + zr * npl;
+    const float mu = __fmul_rn(__fmul_rn(__fadd_rn(u[n], u[n + 1]), -0.5f), dt);
+    const float mv = __fmul_rn(__fmul_rn(__fadd_rn(v[n], v[n + g.P]), -0.5f), dt);
+    const float mw = __fmul_rn(__fmul_rn(__fadd_rn(w[n], w[n + npl]), -0.5f), dt);
+    const float px = __double2float_rn(__dadd_rn(__dadd_rn((double)x, 0.5), (double)mu));
+    const float py = __double2float_rn(__dadd_rn(__dadd_rn((double)y, 0.5), (double)mv));
+    const float pz = __double2float_rn(__dadd_rn(__dadd_rn((double)z, 0.5), (double)mw));
+    const float bx = (float)(unsigned)(g.W - 1), by = (float)(unsigned)(g.H - 1), bz = (float)(unsigned)(g.D - 1);
+    s1[x + y * g.W + zr * cpl] = sample_global32(s0, g.W, cpl, g.zlo, px, py, pz, .5f, .5f, .5f, bx, by, bz, zv, flag);
 }
 
 // ---------------------------------------------------------------------------------------------------

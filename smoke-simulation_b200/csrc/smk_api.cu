@@ -800,7 +800,11 @@ int stage_advect_smoke(smk_sim* s, float dt, int za, int zb, int vlo, int vhi)
     if (zb > za) {
         const int by = 4, bz = 2;
         const dim3 blk(32, by, bz), grd((g.W + 31) / 32, (g.H + by - 1) / by, (zb - za + bz - 1) / bz);
-        smk::k_advect_smoke<<<grd, blk, 0, s->stream>>>(
+        // 32-bit element indices whenever every stored field has fewer than 2^31 elements (SMK_ADVECT_IDX64=1: never)
+        static const bool idx64 = getenv("SMK_ADVECT_IDX64") != nullptr;
+        const bool small = !idx64 && (size_t)g.nplane * g.nzn < ((size_t)1 << 31) && (size_t)g.kplane * g.nzc < ((size_t)1 << 31);
+        auto kern = small ? smk::k_advect_smoke32 : smk::k_advect_smoke;
+        kern<<<grd, blk, 0, s->stream>>>(
             g, s->smoke[n], s->smoke[p], s->u[p], s->v[p], s->w[p], s->code, dt, za, zb, make_int2(vlo, vhi), s->d_flags);
         count_launch(s, SMK_STAGE_ADVECT_SMOKE);
     }
