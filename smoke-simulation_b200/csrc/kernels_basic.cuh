@@ -312,10 +312,13 @@ __device__ __forceinline__ void tri_axis(float pos, float delta, float b, int& i
 {
     const float p = fmaxf(fminf(pos, b), 1.0f);
     const float q = __fadd_rn(p, -delta);
-    i0 = (int)fminf(floorf(q), b);
-    w1 = __fadd_rn(q, -(float)i0);
+    // f0 = (float)i0 and f0 + 1 = (float)(i0 + 1) exactly (integer-valued floats in [0, 2^24)): the int -> float
+    // conversions of the reference expression are skipped, not changed
+    const float f0 = fminf(floorf(q), b);
+    i0 = (int)f0;
+    w1 = __fadd_rn(q, -f0);
     w0 = __fadd_rn(1.0f, -w1);
-    i1 = (int)fminf((float)(i0 + 1), b);
+    i1 = (int)fminf(__fadd_rn(f0, 1.0f), b);
 }
 __device__ __forceinline__ float tri_combine(const Tri& t, float f000, float f100, float f010, float f110,
                                              float f001, float f101, float f011, float f111)
