@@ -43,7 +43,7 @@ TRAFFIC_NCU = {("C2", 1): 366.5e6, ("C2", 4): 423.4e6}  # profiles/r1_v1_pressur
 
 
 def parse_workload(name, gpus):
-    import pyoracle as po
+    from smoke_simulation_b200 import scenes as po
     if name is None:
         name = "C2"
     if name in po.SCENES:
@@ -277,8 +277,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import pyoracle as po
     import smoke_simulation_b200 as smk
+    from smoke_simulation_b200 import scenes as po   # scene definitions only; the oracle is loaded by the cpu_baseline leg alone
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the smoke step has no CPU fallback")
