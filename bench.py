@@ -39,7 +39,7 @@ UNIT = "voxel-steps/s"
 BYTES_PER_CELL_HALFSWEEP = 25  # u,v,w read+write (24 B) + 1 B mask information per cell
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed ncu --set full
 # captures (profiles/): (workload, half-sweeps per launch) -> bytes
-TRAFFIC_NCU = {("C2", 1): 366.5e6, ("C2", 4): 423.4e6}  # profiles/r1_v1_pressure_halfsweep_ncu_full.txt, r1_final_pressure_reg_ncu_full.txt
+TRAFFIC_NCU = {("C2", 1): 366.5e6, ("C2", 4): 420.9e6}  # profiles/r1_v1_pressure_halfsweep_ncu_full.txt, r1_final_pressure_reg_ncu_full.txt
 
 
 def parse_workload(name, gpus):
