@@ -31,6 +31,38 @@ def test_reference_entry_points_are_exported_with_reference_mangling(smk):
     assert abs(g[0] + 9.82) < 1e-6 and b[0] == 2.0
 
 
+def test_a_caller_compiled_against_the_reference_header_links(smk, tmp_path):
+    """A translation unit that includes the REFERENCE's own project/smokeSimulation.cuh (read where it lies; build
+    container only) and calls all nine entry points the way main.cpp / boundingBox.cpp do links against
+    libsmoke_b200.so with a plain host compiler: no source change on the caller's side."""
+    ref_hdr_dir = "/root/reference/project"
+    if not os.path.exists(os.path.join(ref_hdr_dir, "smokeSimulation.cuh")):
+        pytest.skip("reference tree not present (GPU box)")
+    src = tmp_path / "caller.cpp"
+    src.write_text(
+        '#include "smokeSimulation.cuh"\n'
+        "int main(int argc, char**) {\n"
+        "  if (argc > 100) {\n"                      # never executed: this is a link test (no GPU here)
+        "    static float grid[8 * 8 * 8];\n"
+        "    getGPUProperties();\n"
+        "    initializeVolume(grid, 8u, 8u, 8u);\n"
+        "    int a = addSmokeSource(4.f, 4.f, 4.f, 2.f);\n"
+        "    int b = addObstacle(2.f, 2.f, 2.f, 0.f, 0.f, 0.f, 1.f);\n"
+        "    updateObjectPos(a, 3.f, 3.f, 3.f); (void)b;\n"
+        "    *getGravity() = -9.82f; *getBuoyancy() = 2.0f;\n"
+        "    simulate(grid, 0.01f);\n"
+        "    deleteVolume();\n"
+        "  }\n"
+        "  return 0;\n"
+        "}\n")
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(smk.LIB_PATH)
+    r = subprocess.run(["/usr/bin/g++", "-O1", "-x", "c++", str(src), "-I", ref_hdr_dir, "-L", libdir, "-lsmoke_b200",
+                        "-Wl,-rpath," + libdir, "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)], capture_output=True).returncode == 0   # loads the library, calls nothing
+
+
 def test_product_does_not_reference_the_oracle(smk):
     """The product library must not link or embed anything from oracle/."""
     out = subprocess.run(["ldd", smk.LIB_PATH], capture_output=True, text=True).stdout
