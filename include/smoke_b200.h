@@ -58,6 +58,11 @@ enum {
 
 #define SMK_MAX_OBJECTS 16 /* per type; the reference's device arrays hold 3 (cu:56, 221-233) */
 
+/* Threading and device contract (the reference is one thread, one GPU, process-global state, cu:16-58): a handle
+ * belongs to the CUDA device that was current in smk_create(); every entry point switches to that device and restores
+ * the caller's current device before returning, so several handles on several GPUs may live in one process.  A handle
+ * is not thread-safe: serialise calls on the same handle.  Different handles may be used from different threads. */
+
 /* ---- lifetime -------------------------------------------------------------------------------------- */
 
 /* replaces initializeVolume(float* smoke_grid, w, h, d)  (smokeSimulation.cuh:8, cu:124-238).
@@ -139,6 +144,18 @@ int smk_last_pass_ctas(smk_sim* s);
  * the device->host round trip (the result stays on the device; smk_density_device()). */
 int smk_step(smk_sim* s, float dt, float* density_host);
 
+/* Host-buffer contract of smk_step / smk_step_async / smk_read_density_half.  The reference copies into a pageable
+ * std::vector with a blocking cudaMemcpy (cu:814; boundingBox.h:41).  To run that copy at PCIe speed and overlapped with
+ * the last kernels, the library PAGE-LOCKS the caller's range (cudaHostRegister) the first time it sees it and keeps it
+ * locked until smk_unregister_host() or smk_destroy().  A caller that frees or reallocates the buffer while the
+ * handle lives must call smk_unregister_host() first (the drop-in wrappers do: deleteVolume destroys the handle).
+ * A cached registration is re-validated against the driver and against the requested size on every use; buffers the
+ * caller pinned itself (cudaHostAlloc, torch pin_memory) are used as they are.  SMK_NO_HOST_REGISTER=1 in the environment
+ * disables implicit registration (the copy then goes through the driver's pageable path).
+ * smk_register_host() makes the registration explicit (e.g. once, right after allocating the buffer). */
+int smk_register_host(smk_sim* s, void* host, size_t bytes);
+int smk_unregister_host(smk_sim* s, void* host);
+
 /* same, without waiting: returns after enqueueing; smk_sync() waits.  density_host may be NULL.  With a host buffer
  * the readback is PIPELINED: the new density is snapshotted on the device and copied to the host on a second
  * stream while the next step computes (the buffer holds step n's density once step n+1 has been enqueued and
@@ -187,6 +204,15 @@ int smk_index_now(smk_sim* s);
  * reduction (warp shuffles + one atomic per block).  The reference computes no residual. */
 int smk_max_divergence(smk_sim* s, float* out);
 
+/* 64-bit content hashes of the planes this slab OWNS, computed on the device: out7 = {u, v, w "now", u, v, w "past",
+ * density "past"}.  Every element contributes a mix of its bit pattern and its GLOBAL reference-layout index, summed
+ * modulo 2^64, so the sum over all slabs equals the hash of the single-GPU run iff the fields are bit-identical
+ * (-0 counted as +0).  No reference counterpart (the reference is single-GPU and has no checks). */
+int smk_hash_owned(smk_sim* s, unsigned long long* out7);
+/* same over the node planes [node_lo, node_hi) and cell planes [cell_lo, cell_hi) of a handle that stores them (to
+ * hash the slab-shaped parts of a single-GPU run) */
+int smk_hash_range(smk_sim* s, int node_lo, int node_hi, int cell_lo, int cell_hi, unsigned long long* out7);
+
 /* ---- measurement -------------------------------------------------------------------------------------- */
 /* accumulated device time (CUDA events on the step's stream) and launch count per stage since the
  * last smk_reset_timers().  Events are always recorded; reading them synchronises. */
@@ -194,6 +220,9 @@ int smk_stage_time(smk_sim* s, int stage, double* ms_total, long* launches);
 int smk_reset_timers(smk_sim* s);
 /* kernels launched by this handle since creation */
 long smk_launch_count(smk_sim* s);
+/* bytes the steps of this handle have copied device -> host so far (the density readback of cu:814; counted where the
+ * copies are enqueued, so bench.py reports measured, not assumed, bytes per step) */
+unsigned long long smk_readback_bytes(smk_sim* s);
 
 /* ---- multi-GPU halo transport (slab mode) --------------------------------------------------------------- */
 /* Caller-provided exchange: called from smk_step when ghost planes of a field set must be refreshed.

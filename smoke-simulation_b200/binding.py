@@ -82,6 +82,10 @@ def load_library():
     L.smk_step.argtypes = [_vp, _f, _vp]
     L.smk_step_async.argtypes = [_vp, _f, _vp]
     L.smk_sync.argtypes = [_vp]
+    L.smk_register_host.argtypes = [_vp, _vp, C.c_size_t]
+    L.smk_unregister_host.argtypes = [_vp, _vp]
+    L.smk_hash_owned.argtypes = [_vp, C.POINTER(C.c_ulonglong)]
+    L.smk_hash_range.argtypes = [_vp, _i, _i, _i, _i, C.POINTER(C.c_ulonglong)]
     L.smk_density_device.argtypes = [_vp]
     L.smk_density_device.restype = _vp
     L.smk_set_stream.argtypes = [_vp, _vp]
@@ -105,6 +109,8 @@ def load_library():
     L.smk_reset_timers.argtypes = [_vp]
     L.smk_launch_count.argtypes = [_vp]
     L.smk_launch_count.restype = C.c_long
+    L.smk_readback_bytes.argtypes = [_vp]
+    L.smk_readback_bytes.restype = C.c_ulonglong
     L.smk_set_exchange.argtypes = [_vp, EXCHANGE_FN, _vp]
     L.smk_exec_op.argtypes = [_vp, C.POINTER(_i), _f]
     L.smk_p2p_export.argtypes = [_vp, C.c_char_p]
@@ -220,6 +226,8 @@ class SmokeSim:
     def step_async(self, dt, host_ptr=None): self._ck(self.L.smk_step_async(self.h, dt, host_ptr))
     def sync(self): self._ck(self.L.smk_sync(self.h))
     def density_device(self): return self.L.smk_density_device(self.h)
+    def register_host(self, arr): self._ck(self.L.smk_register_host(self.h, arr.ctypes.data_as(_vp), arr.nbytes))
+    def unregister_host(self, arr): self._ck(self.L.smk_unregister_host(self.h, arr.ctypes.data_as(_vp)))
     def copy_density_to_array(self, cuda_array): self._ck(self.L.smk_copy_density_to_array(self.h, cuda_array))
 
     # -- stages
@@ -249,6 +257,19 @@ class SmokeSim:
         self._ck(self.L.smk_max_divergence(self.h, C.byref(v)))
         return float(v.value)
 
+    HASH_NAMES = ("u_now", "v_now", "w_now", "u_past", "v_past", "w_past", "density_past")
+
+    def hash_owned(self):
+        """64-bit content hashes of the owned planes, [u, v, w now, u, v, w past, density past] (device-side)."""
+        out = (C.c_ulonglong * 7)()
+        self._ck(self.L.smk_hash_owned(self.h, out))
+        return [int(v) for v in out]
+
+    def hash_range(self, node_lo, node_hi, cell_lo, cell_hi):
+        out = (C.c_ulonglong * 7)()
+        self._ck(self.L.smk_hash_range(self.h, node_lo, node_hi, cell_lo, cell_hi, out))
+        return [int(v) for v in out]
+
     # -- measurement
     def stage_times(self):
         out = {}
@@ -260,6 +281,7 @@ class SmokeSim:
 
     def reset_timers(self): self._ck(self.L.smk_reset_timers(self.h))
     def launch_count(self): return int(self.L.smk_launch_count(self.h))
+    def readback_bytes(self): return int(self.L.smk_readback_bytes(self.h))
 
     def exec_op(self, op, dt):
         """Run one plan op; `op` = (name-or-kind, a, b, p0, p1) as returned by slab.plan()."""

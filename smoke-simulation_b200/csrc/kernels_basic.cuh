@@ -593,6 +593,39 @@ __global__ void __launch_bounds__(256) k_copy16(float4* __restrict__ dst, const 
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
+// 64-bit content hash of a plane range of one field, independent of how the domain is cut into slabs: every element
+// contributes mix(bit pattern, GLOBAL reference-layout index) and the contributions are summed modulo 2^64 (commutative,
+// so the order of the atomics does not matter).  Used by bench.py / tools to prove that N slabs hold exactly the bits of
+// the single-GPU run at sizes where copying whole fields to the host would be the bottleneck.  -0.0f is hashed as +0.0f
+// (the parity tests compare with ==, which does not tell them apart either).
+__device__ __forceinline__ unsigned long long hash_mix(unsigned bits, unsigned long long idx)
+{
+    if (bits == 0x80000000u) bits = 0u;
+    unsigned long long h = (idx + 0x9E3779B97F4A7C15ull) * 0xBF58476D1CE4E5B9ull;
+    h ^= (unsigned long long)bits * 0x94D049BB133111EBull;
+    h ^= h >> 31; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 29;
+    return h;
+}
+// f: internal layout with row pitch `pitch` and plane stride `plane`, first stored plane zlo; reference-layout row
+// length nx, rows per plane ny; planes [za, zb) are hashed.  One thread per element of a row segment; grid.y = rows, grid.z = planes.
+__global__ void __launch_bounds__(256) k_hash_field(const float* __restrict__ f, int pitch, long long plane, int zlo, int nx, int ny,
+                                                    int za, unsigned long long* __restrict__ out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = za + blockIdx.z;
+    unsigned long long h = 0;
+    if (x < nx) h = hash_mix(__float_as_uint(f[(long long)(z - zlo) * plane + (long long)y * pitch + x]),
+                             ((unsigned long long)z * ny + y) * nx + x);
+    for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    __shared__ unsigned long long sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = h;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += sm[i];
+        atomicAdd(out, t);
+    }
+}
+
 // SURVEY 8(f) N4 (opt-in, off for every parity path): the density as IEEE binary16, round-to-nearest-even, for
 // consumers that want half the device->host bytes.  Two cells per thread.
 __global__ void __launch_bounds__(256) k_density_half(const float* __restrict__ in, __half* __restrict__ out, size_t n)

@@ -102,6 +102,7 @@ struct smk_sim {
     void* exchange_ctx = nullptr;
     int* d_flags = nullptr; // [0]: a backtrace left the valid planes of a slab (SMK_ERR_REACH); [1]: peer wait timed out
     long exchanges = 0;
+    unsigned long long readback_bytes = 0; // bytes the steps copied device -> host so far (smk_readback_bytes)
 
     // one allocation for every exchanged field so that a neighbour process can map it with ONE CUDA IPC handle
     char* arena = nullptr;
@@ -123,8 +124,9 @@ struct smk_sim {
     CUtensorMap tmap[3][3];
     bool tma_ok = false;
 
-    // host buffers registered for fast density readback
-    std::vector<void*> registered;
+    // host ranges this handle page-locked for the density readback (smk_register_host, or implicitly by smk_step)
+    struct HostReg { char* p; size_t bytes; bool implicit; };
+    std::vector<HostReg> registered;
     // pipelined readback (smk_step_async with a host buffer): the new density is snapshotted device-to-device and
     // copied to the host on a second stream while the next step computes
     cudaStream_t copy_stream = nullptr;
@@ -150,10 +152,28 @@ struct smk_sim {
         int nboundary[2];
     };
     std::vector<DevSchedule> schedules;
+    std::vector<const void*> configured; // kernels whose dynamic shared-memory limit has been raised on this handle's device
     std::string err;
 };
 
 namespace {
+
+// Every entry point that touches the device runs on the device the handle was created on and restores the caller's
+// current device afterwards (a second handle on another GPU of the same process, or a caller that
+// changed the current device between calls, used to launch into the wrong context).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(const smk_sim* s)
+    {
+        if (!s) return;
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != s->device) switched = cudaSetDevice(s->device) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (switched) cudaSetDevice(prev);
+    }
+};
 
 thread_local std::string g_last_global_error;
 
@@ -360,6 +380,17 @@ int pick_zchunk(const smk_sim* s, int tiles_xy, int K, int nzn)
 
 int ensure_scratch(smk_sim*) { return SMK_OK; } // the scratch set is part of the arena
 
+// cudaFuncSetAttribute applies to the CURRENT device only: remembered per handle, not per process
+template <typename F>
+int ensure_smem(smk_sim* s, F kern, size_t bytes)
+{
+    const void* key = reinterpret_cast<const void*>(kern);
+    if (std::find(s->configured.begin(), s->configured.end(), key) != s->configured.end()) return SMK_OK;
+    CK(s, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    s->configured.push_back(key);
+    return SMK_OK;
+}
+
 void swap_in_scratch(smk_sim* s)
 {
     const int n = s->now;
@@ -374,13 +405,8 @@ int launch_fused_pass_cfg(smk_sim* s, int sweep0)
 {
     using C = smk::FusedCfg<K, FUSED_NW, FUSED_RPW>;
     const GridP& g = s->g;
-    static bool configured = false;
     auto kern = smk::k_pressure_fused<K, FUSED_NW, FUSED_RPW>;
-    if (!configured) {
-        CK(s, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        configured = true;
-    }
-    int rc = ensure_scratch(s);
+    int rc = ensure_smem(s, kern, C::SMEM);
     if (rc) return rc;
     const int tx = (g.W + 1 + C::OX - 1) / C::OX, ty = (g.SY + C::OY - 1) / C::OY;
     const int zchunk = pick_zchunk(s, tx * ty, K, g.nzn);
@@ -418,11 +444,11 @@ int peer_signal(smk_sim* s, cudaStream_t st) // publish the next epoch: everythi
     return SMK_OK;
 }
 
-int peer_wait(smk_sim* s, cudaStream_t st) // wait until both neighbours published the current epoch
+int peer_wait(smk_sim* s, cudaStream_t st, unsigned target) // wait until both neighbours published `target` (or later)
 {
     unsigned* theirs[2]; const unsigned* mine[2];
     peer_counters(s, theirs, mine);
-    smk::k_epoch_wait<<<1, 1, 0, st>>>(mine[0], mine[1], s->epoch, s->d_flags, (long long)2e10);
+    smk::k_epoch_wait<<<1, 1, 0, st>>>(mine[0], mine[1], target, s->d_flags, (long long)2e10);
     s->launches++;
     CK(s, cudaGetLastError());
     return SMK_OK;
@@ -435,7 +461,26 @@ int peer_sync(smk_sim* s)
     if (nosync) return SMK_OK;
     int rc = peer_signal(s, s->stream);
     if (rc) return rc;
-    return peer_wait(s, s->stream);
+    return peer_wait(s, s->stream, s->epoch);
+}
+
+// Epoch accounting of a pressure pass that reads neighbour planes.  EVERY branch of launch_reg_pass consumes exactly two
+// epoch values per pass -- E_pre = "everything I enqueued before this pass is final" and E_post = "my boundary planes of
+// this pass are written and I no longer read yours" -- whatever schedule the rank picked for its own plane count
+// (in-kernel handshake, boundary chunks on a second stream, or a plain stream-level handshake), so neighbours whose
+// slabs differ by a plane and therefore chunk differently still agree on every value (the branches used to
+// advance the epoch by 2, 1 and 1).  Waits are ">= target", and a later value implies every earlier one.
+// The stream-level branches publish E_pre and leave E_post to be implied by the next value they publish; they wait for
+// E_pre in front of the first pass of a step (the neighbour's advection and fill must be covered) and for the previous
+// pass's E_post otherwise (an in-kernel neighbour publishes nothing else between two passes).
+unsigned stream_pass_epochs(smk_sim* s, int sweep0, cudaStream_t wait_stream, int* rc)
+{
+    *rc = peer_signal(s, s->stream);                 // E_pre
+    const unsigned pre = s->epoch;
+    s->epoch++;                                      // E_post: implied by whatever this rank publishes next
+    s->pass_epoch_next = -1;
+    if (*rc == SMK_OK) *rc = peer_wait(s, wait_stream, sweep0 == 0 ? pre : pre - 1);
+    return pre;
 }
 
 // pointer to the (virtual) plane 0 of a field whose first stored plane is zlo; never dereferenced outside the stored planes
@@ -495,13 +540,11 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
 {
     using C = smk::RegCfg<K, NW>;
     const GridP& g = s->g;
-    static bool configured = false;
-    if (!configured) {
-        CK(s, cudaFuncSetAttribute(smk::k_pressure_reg<K, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        CK(s, cudaFuncSetAttribute(smk::k_pressure_reg<K, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        CK(s, cudaFuncSetAttribute(smk::k_pressure_reg_bal<K, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        CK(s, cudaFuncSetAttribute(smk::k_pressure_reg_bal<K, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        configured = true;
+    {
+        int rc0;
+        if ((rc0 = ensure_smem(s, smk::k_pressure_reg<K, NW, false>, C::SMEM)) || (rc0 = ensure_smem(s, smk::k_pressure_reg<K, NW, true>, C::SMEM)) ||
+            (rc0 = ensure_smem(s, smk::k_pressure_reg_bal<K, NW, false>, C::SMEM)) || (rc0 = ensure_smem(s, smk::k_pressure_reg_bal<K, NW, true>, C::SMEM)))
+            return rc0;
     }
     // forcing + clamp deferred to this pass (exec_op / stage_pressure): the first pass of the step applies them on load
     const bool force = s->pending_force;
@@ -587,11 +630,15 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
             CK(s, cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
             CK(s, cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
         }
+        // (the signal is enqueued on the main stream in front of the fork; the wait goes to the second stream)
         int rc = peer_signal(s, s->stream);
         if (rc) return rc;
+        const unsigned pre = s->epoch;
+        s->epoch++; // E_post (see stream_pass_epochs)
+        s->pass_epoch_next = -1;
         CK(s, cudaEventRecord(s->ev_fork, s->stream));
         CK(s, cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0));
-        if ((rc = peer_wait(s, s->aux_stream))) return rc;
+        if ((rc = peer_wait(s, s->aux_stream, sweep0 == 0 ? pre : pre - 1))) return rc;
         smk::PassRange pb = pr;
         pb.chunk_first = 0; pb.chunk_step = nchunks - 1;
         kern<<<dim3((unsigned)tx, (unsigned)ty, 2u), C::THREADS, C::SMEM, s->aux_stream>>>(
@@ -605,7 +652,9 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
         s->launches++;
     } else {
         if (from_peers) {
-            int rc = peer_sync(s);
+            static const bool nosync = getenv("SMK_DBG_NOSYNC") != nullptr; // timing experiments only (races!)
+            int rc = SMK_OK;
+            if (!nosync) stream_pass_epochs(s, sweep0, s->stream, &rc);
             if (rc) return rc;
         }
         // Default: the (tile, z-chunk) grid.  Opt-in (smk_set_pass_ctas / SMK_PASS_CTAS=n): n CTAs working through piece
@@ -764,11 +813,7 @@ int stage_advect_velocity(smk_sim* s, float dt, int za, int zb, int vlo, int vhi
         if (use_tma && s->tma_ok) {
             // TMA-staged tiles (kernels_advect_tma.cuh): tile + halo planes land in shared memory, gathers are LDS
             using A = smk::AdvTma;
-            static bool configured = false;
-            if (!configured) {
-                CK(s, cudaFuncSetAttribute(smk::k_advect_velocity_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A::SMEM));
-                configured = true;
-            }
+            if (int rc0 = ensure_smem(s, smk::k_advect_velocity_tma, A::SMEM)) return rc0;
             const int id = s->vel_id[n];
             const int tiles = ((g.W + A::TX - 1) / A::TX) * ((g.H + A::TY - 1) / A::TY);
             int zchunk = zb - za; // enough CTAs for ~8 per SM, chunks of at least 16 planes (5 lead-in planes each)
@@ -818,19 +863,46 @@ void flip(smk_sim* s) // cu:777-779
     s->now = s->now == 0 ? 1 : 0;
 }
 
-bool try_register(smk_sim* s, void* p, size_t bytes)
+// Page-lock [p, p + bytes) so that the device->host copy of the density runs at PCIe speed and asynchronously.
+// The library cannot know the lifetime of a caller's buffer: an entry is trusted only if it covers the
+// requested range AND the driver still reports the range as registered host memory; a stale entry (the caller freed
+// the buffer, or reuses the address with another size) is dropped and the range registered afresh.  Implicit
+// registrations are released by smk_destroy or by smk_unregister_host; the contract is in smoke_b200.h.
+bool range_is_pinned(const void* p)
 {
-    if (std::find(s->registered.begin(), s->registered.end(), p) != s->registered.end()) return true;
-    static const bool off = getenv("SMK_NO_HOST_REGISTER") != nullptr;
-    if (off) return false;
     cudaPointerAttributes at{};
-    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) return true; // already pinned
+    const bool ok = cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost;
     cudaGetLastError();
+    return ok;
+}
+
+void drop_registration(smk_sim* s, size_t i)
+{
+    if (range_is_pinned(s->registered[i].p)) cudaHostUnregister(s->registered[i].p);
+    cudaGetLastError();
+    s->registered.erase(s->registered.begin() + (long)i);
+}
+
+bool try_register(smk_sim* s, void* vp, size_t bytes, bool implicit = true)
+{
+    char* p = static_cast<char*>(vp);
+    if (!p || bytes == 0) return false;
+    for (size_t i = 0; i < s->registered.size();) {
+        auto& r = s->registered[i];
+        const bool overlaps = p < r.p + r.bytes && r.p < p + bytes;
+        if (!overlaps) { i++; continue; }
+        const bool covers = r.p <= p && p + bytes <= r.p + r.bytes;
+        if (covers && range_is_pinned(p) && range_is_pinned(p + bytes - 1)) return true;
+        drop_registration(s, i); // stale or partial: register the requested range afresh
+    }
+    static const bool off = getenv("SMK_NO_HOST_REGISTER") != nullptr;
+    if (off && implicit) return false;
+    if (range_is_pinned(p) && range_is_pinned(p + bytes - 1)) return true; // pinned by the caller (cudaHostAlloc / torch pin_memory)
     if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
-    s->registered.push_back(p);
+    s->registered.push_back({p, bytes, implicit});
     return true;
 }
 
@@ -951,10 +1023,16 @@ int exchange_overlapped_with_advect(smk_sim* s, const slab::Op& adv, float dt, b
         CK(s, cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
         CK(s, cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
     }
+    // One epoch value per exchange op of the plan, as in the non-overlapped execution (a neighbour whose slab is too
+    // thin to overlap runs the two exchanges separately and must find the same values): pulling the density together
+    // with u, v, w consumes the density exchange's value too.  It is published at once -- the density "now" has been
+    // final since the fill -- and a later value implies the earlier one for a neighbour that waits for it.
+    const unsigned first = s->epoch + 1;
+    if (with_smoke) s->epoch++;
     if ((rc = peer_signal(s, s->stream))) return rc;
     CK(s, cudaEventRecord(s->ev_fork, s->stream));
     CK(s, cudaStreamWaitEvent(s->aux_stream, s->ev_fork, 0));
-    if ((rc = peer_wait(s, s->aux_stream))) return rc;
+    if ((rc = peer_wait(s, s->aux_stream, first))) return rc;
     if ((rc = p2p_pull(s, slab::SET_VEL_NOW, s->aux_stream))) return rc;
     if (with_smoke && (rc = p2p_pull(s, slab::SET_SMOKE_NOW, s->aux_stream))) return rc;
     CK(s, cudaEventRecord(s->ev_join, s->aux_stream));
@@ -983,6 +1061,11 @@ int enqueue_step(smk_sim* s, float dt, float* density_host, bool pipelined = fal
     const size_t nops = split ? ops.size() - 1 : ops.size();
     bool smoke_pulled = false;
     for (size_t i = 0; i < nops && rc == SMK_OK; i++) {
+        // Peer-memory path: the fill stamps the sources into BOTH density buffers, one of which the neighbours pulled
+        // ghost planes from at the end of their previous step.  One handshake in front of the fill -- "my pulls of your
+        // previous-step planes are done" -- keeps a neighbour that runs ahead from stamping a moved source under a pull
+        // that is still in flight.  (Every rank does it, so the epoch values stay aligned.)
+        if (ops[i].kind == slab::OP_FILL && s->p2p && s->geom.world > 1 && (rc = peer_sync(s))) break;
         if (ops[i].kind == slab::OP_EXCHANGE && ops[i].a == slab::SET_SMOKE_NOW && smoke_pulled) continue;
         if (ops[i].kind == slab::OP_EXCHANGE && ops[i].a == slab::SET_VEL_NOW && i + 1 < ops.size() &&
             ops[i + 1].kind == slab::OP_ADVECT_VEL && overlap_exchange_ok(s, ops[i + 1])) {
@@ -1017,6 +1100,7 @@ int enqueue_step(smk_sim* s, float dt, float* density_host, bool pipelined = fal
             const int pa = i == 0 ? c0 : a, pb = i == nch - 1 ? c1 : b;
             CK(s, cudaMemcpyAsync(density_host + (size_t)pa * g.cplane, s->smoke[s->past] + (size_t)(pa - g.zlo) * g.cplane,
                                   (size_t)(pb - pa) * g.cplane * sizeof(float), cudaMemcpyDeviceToHost, s->copy_stream));
+            s->readback_bytes += (size_t)(pb - pa) * g.cplane * sizeof(float);
         }
         Span sp(s, SMK_STAGE_READBACK);
         CK(s, cudaEventRecord(s->ev_copied, s->copy_stream));
@@ -1030,6 +1114,7 @@ int enqueue_step(smk_sim* s, float dt, float* density_host, bool pipelined = fal
         float* dst = density_host + (size_t)s->geom.c0 * g.cplane;
         try_register(s, dst, bytes);
         const float* src = s->smoke[s->past] + (size_t)(s->geom.c0 - g.zlo) * g.cplane;
+        s->readback_bytes += bytes;
         if (!pipelined) {
             CK(s, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s->stream));
         } else {
@@ -1301,7 +1386,7 @@ int smk_pass_schedule(unsigned W, unsigned H, int out_lo, int out_hi, int K, int
 }
 
 int smk_destroy(smk_sim* s)
-{
+{ DeviceGuard dg(s);
     if (!s) return SMK_ERR_ARG;
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
@@ -1313,7 +1398,7 @@ int smk_destroy(smk_sim* s)
     if (s->ev_copied) cudaEventDestroy(s->ev_copied);
     cudaFree(s->snapshot);
     cudaFree(s->half_stage);
-    for (void* p : s->registered) cudaHostUnregister(p);
+    while (!s->registered.empty()) drop_registration(s, s->registered.size() - 1);
     for (auto& sp : s->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
     for (auto e : s->free_events) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++)
@@ -1407,7 +1492,7 @@ int smk_set_pass_ctas(smk_sim* s, int nctas)
 int smk_last_pass_ctas(smk_sim* s) { return s ? s->last_pass_ctas : -SMK_ERR_ARG; }
 
 int smk_set_stream(smk_sim* s, void* cuda_stream)
-{
+{ DeviceGuard dg(s);
     if (!s) return SMK_ERR_ARG;
     CK(s, cudaStreamSynchronize(s->stream));
     int rc = fold_timers(s);
@@ -1424,17 +1509,17 @@ int smk_set_stream(smk_sim* s, void* cuda_stream)
 }
 
 int smk_step_async(smk_sim* s, float dt, float* density_host)
-{
+{ DeviceGuard dg(s);
     if (!s) return SMK_ERR_ARG;
     return enqueue_step(s, dt, density_host, true);
 }
 
 int smk_sync(smk_sim* s)
-{
+{ DeviceGuard dg(s);
     if (!s) return SMK_ERR_ARG;
     CK(s, cudaStreamSynchronize(s->stream));
     if (s->copy_pending) { CK(s, cudaStreamSynchronize(s->copy_stream)); s->copy_pending = false; }
-    if (s->geom.world > 1) { // slab runs: did a backtrace leave the valid planes?
+    { // device-side error flags: [0] backtrace left the valid planes (slab runs), [1] peer wait timed out, [2] TMA timeout (any run)
         int flag[3] = {0, 0, 0};
         CK(s, cudaMemcpy(flag, s->d_flags, sizeof(flag), cudaMemcpyDeviceToHost));
         if (flag[0] || flag[1] || flag[2]) cudaMemset(s->d_flags, 0, sizeof(flag));
@@ -1448,7 +1533,7 @@ int smk_sync(smk_sim* s)
 }
 
 int smk_step(smk_sim* s, float dt, float* density_host)
-{
+{ DeviceGuard dg(s);
     if (!s) return SMK_ERR_ARG;
     int rc = enqueue_step(s, dt, density_host);
     if (rc) return rc;
@@ -1457,10 +1542,33 @@ int smk_step(smk_sim* s, float dt, float* density_host)
 
 const float* smk_density_device(smk_sim* s) { return s ? s->smoke[s->past] : nullptr; }
 
+int smk_register_host(smk_sim* s, void* host, size_t bytes)
+{
+    if (!s || !host || bytes == 0) return SMK_ERR_ARG;
+    DeviceGuard dg(s);
+    if (!try_register(s, host, bytes, false)) return fail(s, SMK_ERR_CUDA, "cudaHostRegister failed for the caller's buffer");
+    return SMK_OK;
+}
+
+int smk_unregister_host(smk_sim* s, void* host)
+{
+    if (!s || !host) return SMK_ERR_ARG;
+    DeviceGuard dg(s);
+    CK(s, cudaStreamSynchronize(s->stream));
+    if (s->copy_stream) CK(s, cudaStreamSynchronize(s->copy_stream));
+    char* p = static_cast<char*>(host);
+    for (size_t i = 0; i < s->registered.size(); i++)
+        if (s->registered[i].p <= p && p < s->registered[i].p + s->registered[i].bytes) {
+            drop_registration(s, i);
+            return SMK_OK;
+        }
+    return SMK_OK; // not registered by this handle: nothing to do
+}
+
 // this slab's owned planes of the last step's density as binary16 -- converted on the device
 // (round to nearest even), half the bytes over PCIe.  Blocking.  Never used by the drop-in entry points.
 int smk_read_density_half(smk_sim* s, void* host_half)
-{
+{ DeviceGuard dg(s);
     if (!s || !host_half) return SMK_ERR_ARG;
     const GridP& g = s->g;
     const size_t n = (size_t)(s->geom.c1 - s->geom.c0) * g.cplane;
@@ -1479,7 +1587,7 @@ int smk_read_density_half(smk_sim* s, void* host_half)
 // (cudaGraphicsGLRegisterImage on m_gridTex -> cudaGraphicsSubResourceGetMappedArray) the new density goes straight
 // into that array: one device-to-device 3-D copy on the step's stream, no host round trip.
 int smk_copy_density_to_array(smk_sim* s, void* cuda_array)
-{
+{ DeviceGuard dg(s);
     if (!s || !cuda_array) return SMK_ERR_ARG;
     const GridP& g = s->g;
     cudaMemcpy3DParms p{};
@@ -1511,23 +1619,23 @@ int smk_test_array_read(void* cuda_array, float* host, unsigned W, unsigned H, u
 }
 void smk_test_array_destroy(void* cuda_array) { cudaFreeArray(static_cast<cudaArray_t>(cuda_array)); }
 
-int smk_stage_flip(smk_sim* s) { if (!s) return SMK_ERR_ARG; flip(s); return SMK_OK; }
-int smk_stage_fill(smk_sim* s) { return s ? stage_fill(s) : SMK_ERR_ARG; }
-int smk_stage_force_clamp(smk_sim* s, float dt) { return s ? stage_force_clamp(s, dt, s->g.zlo, s->g.zlo + s->g.nzn) : SMK_ERR_ARG; }
+int smk_stage_flip(smk_sim* s) { DeviceGuard dg(s); if (!s) return SMK_ERR_ARG; flip(s); return SMK_OK; }
+int smk_stage_fill(smk_sim* s) { DeviceGuard dg(s); return s ? stage_fill(s) : SMK_ERR_ARG; }
+int smk_stage_force_clamp(smk_sim* s, float dt) { DeviceGuard dg(s); return s ? stage_force_clamp(s, dt, s->g.zlo, s->g.zlo + s->g.nzn) : SMK_ERR_ARG; }
 int smk_stage_pressure_halfsweep(smk_sim* s, int offset)
-{
+{ DeviceGuard dg(s);
     if (!s) return SMK_ERR_ARG;
     Span sp(s, SMK_STAGE_PRESSURE);
     launch_halfsweep(s, offset & 1);
     CK(s, cudaGetLastError());
     return SMK_OK;
 }
-int smk_stage_pressure(smk_sim* s) { return s ? stage_pressure(s) : SMK_ERR_ARG; }
-int smk_stage_advect_velocity(smk_sim* s, float dt) { return s ? stage_advect_velocity(s, dt, s->g.zlo, s->g.zlo + s->g.nzn, s->g.zlo, s->g.zlo + s->g.nzn - 1) : SMK_ERR_ARG; }
-int smk_stage_advect_smoke(smk_sim* s, float dt) { return s ? stage_advect_smoke(s, dt, s->g.zlo, s->g.zlo + s->g.nzc, s->g.zlo, s->g.zlo + s->g.nzc - 1) : SMK_ERR_ARG; }
+int smk_stage_pressure(smk_sim* s) { DeviceGuard dg(s); return s ? stage_pressure(s) : SMK_ERR_ARG; }
+int smk_stage_advect_velocity(smk_sim* s, float dt) { DeviceGuard dg(s); return s ? stage_advect_velocity(s, dt, s->g.zlo, s->g.zlo + s->g.nzn, s->g.zlo, s->g.zlo + s->g.nzn - 1) : SMK_ERR_ARG; }
+int smk_stage_advect_smoke(smk_sim* s, float dt) { DeviceGuard dg(s); return s ? stage_advect_smoke(s, dt, s->g.zlo, s->g.zlo + s->g.nzc, s->g.zlo, s->g.zlo + s->g.nzc - 1) : SMK_ERR_ARG; }
 
 int smk_get_field(smk_sim* s, int field, int which, void* host_dst)
-{
+{ DeviceGuard dg(s);
     if (!s || !host_dst) return SMK_ERR_ARG;
     FieldRef f;
     if (field_ref(s, field, which, &f)) return fail(s, SMK_ERR_ARG, "bad field / buffer selector");
@@ -1535,7 +1643,7 @@ int smk_get_field(smk_sim* s, int field, int which, void* host_dst)
 }
 
 int smk_set_field(smk_sim* s, int field, int which, const void* host_src)
-{
+{ DeviceGuard dg(s);
     if (!s || !host_src) return SMK_ERR_ARG;
     FieldRef f;
     if (field_ref(s, field, which, &f)) return fail(s, SMK_ERR_ARG, "bad field / buffer selector");
@@ -1555,7 +1663,7 @@ int smk_index_now(smk_sim* s) { return s ? s->now : -1; }
 
 // ---- peer-memory halo path (CUDA IPC between the per-GPU processes, or plain pointers inside one process) ----
 int smk_p2p_export(smk_sim* s, unsigned char* handle64)
-{
+{ DeviceGuard dg(s);
     if (!s || !handle64) return SMK_ERR_ARG;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
     cudaIpcMemHandle_t h;
@@ -1577,7 +1685,7 @@ static int attach_common(smk_sim* s, int side, char* arena, bool ipc)
 }
 
 int smk_p2p_attach_ipc(smk_sim* s, int side, const unsigned char* handle64)
-{
+{ DeviceGuard dg(s);
     if (!s || !handle64 || side < 0 || side > 1) return SMK_ERR_ARG;
     if ((side == 0 && !s->geom.has_lower()) || (side == 1 && !s->geom.has_upper())) return fail(s, SMK_ERR_ARG, "no neighbour on that side");
     cudaIpcMemHandle_t h;
@@ -1600,7 +1708,7 @@ long smk_exchange_count(smk_sim* s) { return s ? s->exchanges : -1; }
 // thread on one GPU (tests): there all signals of a synchronisation point must be enqueued before any wait, because
 // streams may share a hardware queue and a spinning wait would block a signal queued behind it.
 int smk_p2p_presignal(smk_sim* s)
-{
+{ DeviceGuard dg(s);
     if (!s || !s->p2p) return SMK_ERR_ARG;
     unsigned* theirs[2]; const unsigned* mine[2];
     peer_counters(s, theirs, mine);
@@ -1611,13 +1719,13 @@ int smk_p2p_presignal(smk_sim* s)
 }
 
 int smk_exec_op(smk_sim* s, const int* op5, float dt)
-{
+{ DeviceGuard dg(s);
     if (!s || !op5) return SMK_ERR_ARG;
     return exec_op(s, slab::Op{op5[0], op5[1], op5[2], op5[3], op5[4]}, dt);
 }
 
 int smk_max_divergence(smk_sim* s, float* out)
-{
+{ DeviceGuard dg(s);
     if (!s || !out) return SMK_ERR_ARG;
     const GridP& g = s->g;
     int za, zb;
@@ -1636,8 +1744,42 @@ int smk_max_divergence(smk_sim* s, float* out)
     return SMK_OK;
 }
 
-int smk_stage_time(smk_sim* s, int stage, double* ms_total, long* launches)
+// 64-bit content hashes of this slab's OWNED planes (k_hash_field): out7 = {u, v, w "now", u, v, w "past", density "past"}.
+// Summing the values of all slabs (mod 2^64) gives the hash of the whole domain, whatever the decomposition.
+int smk_hash_range(smk_sim* s, int nlo, int nhi, int clo, int chi, unsigned long long* out7)
 {
+    if (!s || !out7) return SMK_ERR_ARG;
+    DeviceGuard dg(s);
+    const GridP& g = s->g;
+    if (nlo < g.zlo || nhi > g.zlo + g.nzn || clo < g.zlo || chi > g.zlo + g.nzc) return fail(s, SMK_ERR_ARG, "smk_hash_range: planes not stored by this handle");
+    unsigned long long* d = nullptr;
+    CK(s, cudaMalloc(&d, 7 * sizeof(unsigned long long)));
+    CK(s, cudaMemsetAsync(d, 0, 7 * sizeof(unsigned long long), s->stream));
+    const float* nodes[6] = {s->u[s->now], s->v[s->now], s->w[s->now], s->u[s->past], s->v[s->past], s->w[s->past]};
+    for (int i = 0; i < 6 && nhi > nlo; i++) {
+        const dim3 grid((unsigned)((g.W + 1 + 255) / 256), (unsigned)(g.H + 1), (unsigned)(nhi - nlo));
+        smk::k_hash_field<<<grid, 256, 0, s->stream>>>(nodes[i], g.P, g.nplane, g.zlo, g.W + 1, g.H + 1, nlo, d + i);
+    }
+    if (chi > clo) {
+        const dim3 grid((unsigned)((g.W + 255) / 256), (unsigned)g.H, (unsigned)(chi - clo));
+        smk::k_hash_field<<<grid, 256, 0, s->stream>>>(s->smoke[s->past], g.W, g.cplane, g.zlo, g.W, g.H, clo, d + 6);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out7, d, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(s, SMK_ERR_CUDA, std::string("smk_hash_range: ") + cudaGetErrorString(e));
+    return SMK_OK;
+}
+
+int smk_hash_owned(smk_sim* s, unsigned long long* out7)
+{
+    if (!s) return SMK_ERR_ARG;
+    return smk_hash_range(s, s->geom.own_node_lo(), s->geom.own_node_hi() + 1, s->geom.c0, s->geom.c1, out7);
+}
+
+int smk_stage_time(smk_sim* s, int stage, double* ms_total, long* launches)
+{ DeviceGuard dg(s);
     if (!s || stage < 0 || stage >= SMK_STAGE_COUNT) return SMK_ERR_ARG;
     int rc = fold_timers(s);
     if (rc) return rc;
@@ -1647,7 +1789,7 @@ int smk_stage_time(smk_sim* s, int stage, double* ms_total, long* launches)
 }
 
 int smk_reset_timers(smk_sim* s)
-{
+{ DeviceGuard dg(s);
     if (!s) return SMK_ERR_ARG;
     int rc = fold_timers(s);
     if (rc) return rc;
@@ -1656,6 +1798,7 @@ int smk_reset_timers(smk_sim* s)
 }
 
 long smk_launch_count(smk_sim* s) { return s ? s->launches : -1; }
+unsigned long long smk_readback_bytes(smk_sim* s) { return s ? s->readback_bytes : 0; }
 
 int smk_set_exchange(smk_sim* s, smk_exchange_fn fn, void* ctx)
 {

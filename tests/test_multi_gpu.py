@@ -20,7 +20,7 @@ def _ngpu():
         return 0
 
 
-@pytest.mark.parametrize("transport,dims", [("p2p", (64, 48, 40)), ("p2p", (70, 33, 24)), ("nccl", (64, 48, 40))])
+@pytest.mark.parametrize("transport,dims", [("p2p", (64, 48, 40)), ("p2p", (70, 33, 24)), ("nccl", (64, 48, 40)), ("p2p", (256, 256, 80))])
 def test_slabs_across_processes_bit_identical(transport, dims):
     n = _ngpu()
     if n < 2:

@@ -67,14 +67,17 @@ def test_virtual_slabs_bit_identical_to_single_gpu(po, smk, world, ghost, fuse, 
 
 
 @pytest.mark.parametrize("world,ghost,fuse,dims", [(2, 8, 4, (70, 40, 48)), (4, 4, 4, (40, 30, 64)), (3, 5, 4, (60, 37, 41)),
-                                                   (2, 6, 2, (20, 18, 30))])
+                                                   (2, 6, 2, (20, 18, 30)), (2, 8, 4, (256, 256, 160))])
 @pytest.mark.parametrize("ctas", [0, 3, 148])
 def test_peer_memory_path_bit_identical_to_single_gpu(po, smk, world, ghost, fuse, dims, ctas):
     """The B200-native transport: pressure passes read the neighbours' boundary planes straight from their memory
     (epoch handshake per pass, no ghost copies), halo refreshes before advection are pulls over the mapped memory.
     Virtual slabs in one process (pointer attach instead of CUDA IPC); every rank just runs smk_step_async.
     ctas: schedule of a pass -- the (tile, z-chunk) grid (0, default) or balanced piece lists on 3 / 148 CTAs (boundary
-    pieces first, in-kernel handshake per piece)."""
+    pieces first, in-kernel handshake per piece).
+    256x256x160 on two slabs is the case ADVICE r1 names: the slabs own 80 and 81 node planes, which chunk differently
+    (2 chunks -> stream-level handshake on one rank, 5 chunks -> in-kernel handshake on the other); both must consume the
+    same epoch values per pass."""
     from smoke_simulation_b200 import slab
     W, H, D = dims
     iterations, steps, dt = 7, 3, 0.05
