@@ -32,6 +32,15 @@ enum : unsigned {
     CODE_SELF = 128u   // the cell itself is fluid
 };
 
+// Second encoding of the same information for the fused pressure passes ("pcode", one byte per cell, same pitch):
+// bits 0-5 as above, bit 6 = ACTIVE, bit 7 = COMPLEX for an ACTIVE cell (fewer than six fluid neighbours: the update
+// needs the per-face masks and its own neighbour count) and = SELF for a cell that is not ACTIVE.  So
+//   (p & 0xC0) == 0x40   ACTIVE with six fluid neighbours  -> acc = 6, every face updated (the common case),
+//   (p & 0xC0) == 0xC0   ACTIVE next to a solid / the domain shell -> general update,
+//   (p & 0xC0) != 0      the cell is fluid (what the forcing term needs, cu:321),
+// and a warp decides "every cell of this sweep is ACTIVE and simple" with one LOP3 + one vote.
+enum : unsigned { PCODE_ACTIVE = 64u, PCODE_COMPLEX = 128u };
+
 #define SMK_MAX_OBJ 16
 struct ObjP {
     int nsrc, nobs;

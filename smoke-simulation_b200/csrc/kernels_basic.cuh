@@ -106,8 +106,21 @@ __global__ void __launch_bounds__(256) k_fill_sources(GridP g, float* __restrict
 // and the "both cells fluid" tests of integrate / advection (cu:321, 534, 564, 594, 623) into one byte
 // per cell so that the hot kernels read 1 B/cell of mask information.  Neighbours outside the domain (or
 // outside the stored slab) count as solid; such cells are never ACTIVE.
+// "This plane holds a COMPLEX cell inside tile (bx, by)" for the tile geometry of the K = 4 fused pass (56 x 24 output
+// cells, 4-cell halo: tile b loads cells [56 bx - 4, 56 bx + 60) x [24 by - 4, 24 by + 28)): cflag[z - zlo][by][bx] = 1.
+// A CTA of the pass whose planes carry no flag runs the variant without the general update (kernels_pressure_tma.cuh).
+struct TileFlags { unsigned char* f; int tx, ty; };
+__device__ __forceinline__ void mark_complex(const TileFlags& tf, int x, int y, int zrel)
+{
+    if (!tf.f) return;
+    const int bx1 = min((x + 4) / 56, tf.tx - 1), bx0 = max(0, (x - 59 + 55) / 56);
+    const int by1 = min((y + 4) / 24, tf.ty - 1), by0 = max(0, (y - 27 + 23) / 24);
+    for (int by = by0; by <= by1; by++)
+        for (int bx = bx0; bx <= bx1; bx++) tf.f[((long long)zrel * tf.ty + by) * tf.tx + bx] = 1;
+}
+
 __global__ void __launch_bounds__(256) k_codes(GridP g, const unsigned char* __restrict__ mask,
-                                               unsigned char* __restrict__ code, int za)
+                                               unsigned char* __restrict__ code, unsigned char* __restrict__ pcode, int za, TileFlags tf)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.W * g.H) return;
@@ -125,14 +138,18 @@ __global__ void __launch_bounds__(256) k_codes(GridP g, const unsigned char* __r
     const bool interior = x >= 1 && y >= 1 && z >= 1 && x < g.W - 1 && y < g.H - 1 && z < g.D - 1;
     const bool self = mask[c] != 0;
     if (self) v |= CODE_SELF;
-    if (interior && self && (v & 63u)) v |= CODE_ACTIVE;
+    const bool active = interior && self && (v & 63u);
+    if (active) v |= CODE_ACTIVE;
     code[code_index(g, x, y, z)] = (unsigned char)v;
+    const unsigned m6 = v & 63u;
+    pcode[code_index(g, x, y, z)] = (unsigned char)(m6 | (active ? PCODE_ACTIVE : 0u) | ((active ? m6 != 63u : self) ? PCODE_COMPLEX : 0u));
+    if (active && m6 != 63u) mark_complex(tf, x, y, z - g.zlo);
 }
 
 // Four cells per thread (W % 4 == 0): the mask rows are read as 32-bit words (bytes are 0/1), the six neighbour
 // bits of the four cells are assembled with whole-word arithmetic, one 32-bit store.  7 loads per 4 cells instead of 28.
 __global__ void __launch_bounds__(256) k_codes4(GridP g, const unsigned char* __restrict__ mask,
-                                                unsigned char* __restrict__ code, int za)
+                                                unsigned char* __restrict__ code, unsigned char* __restrict__ pcode, int za, TileFlags tf)
 {
     const int W4 = g.W >> 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,7 +176,12 @@ __global__ void __launch_bounds__(256) k_codes4(GridP g, const unsigned char* __
         if (x == 0) interior &= ~0xffu;
         if (x + 4 == g.W) interior &= ~0xff000000u;
     }
-    v |= cs * CODE_SELF | (any_nb & cs & interior) * CODE_ACTIVE;
+    const unsigned act = any_nb & cs & interior;                // per byte 0/1: ACTIVE
+    const unsigned full = ((v + b) >> 6) & b;                   // per byte: all six neighbours fluid (0x3f + 1 = 0x40)
+    const unsigned hi = (act & ~full) | (~act & cs & b);        // pcode bit 7: COMPLEX if ACTIVE, else SELF
+    *reinterpret_cast<unsigned*>(pcode + code_index(g, x, y, z)) = v | act * PCODE_ACTIVE | hi * PCODE_COMPLEX;
+    if (act & hi) mark_complex(tf, x, y, z - g.zlo); // (tile borders are multiples of 4 in x: the quad lies in the same tiles)
+    v |= cs * CODE_SELF | act * CODE_ACTIVE;
     *reinterpret_cast<unsigned*>(code + code_index(g, x, y, z)) = v;
 }
 

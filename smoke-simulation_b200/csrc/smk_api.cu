@@ -22,6 +22,8 @@
 #include "kernels_basic.cuh"
 #include "kernels_pressure_fused.cuh"
 #include "kernels_pressure_reg.cuh"
+#include "kernels_pressure_lean.cuh"
+#include "kernels_pressure_tma.cuh"
 #include "kernels_advect_tma.cuh"
 #include "kernels_jacobi.cuh"
 #include "slab_plan.h"
@@ -75,6 +77,9 @@ struct smk_sim {
     float* scratch[3]{}; // second u,v,w set for the out-of-place fused pressure passes (lazy)
     unsigned char* mask = nullptr;
     unsigned char* code = nullptr;
+    unsigned char* pcode = nullptr; // the same stencil information in the encoding of the fused pressure passes (grid.h)
+    unsigned char* cflag = nullptr; // [stored cell plane][tile y][tile x]: the plane holds a COMPLEX cell inside that K = 4 tile
+    int cflag_tx = 0, cflag_ty = 0;
     int num_sms = 148;
     unsigned* d_scalar = nullptr; // device scratch for reductions
 
@@ -85,6 +90,8 @@ struct smk_sim {
 
     int solver = SMK_SOLVER_RBGS;
     int pass_epoch_next = -1;   // half-sweep index whose handshake epoch the previous pass kernel publishes itself
+    bool want_maxw = false;     // the next fused pass also reduces max |w| over the planes it writes into d_dyn[0]
+    unsigned* d_dyn = nullptr;  // device words: [0] max |w| bits (atomicMax), [1] advection margin in planes
     bool pending_force = false; // forcing + clamp of this step are applied by the first pressure pass (fused)
     float pending_dt = 0.f;
     int pending_a = 0, pending_b = 0;
@@ -123,6 +130,14 @@ struct smk_sim {
     // TMA descriptors of the three physical buffers of u, v, w (box = advection tile + halo), [field][physical id]
     CUtensorMap tmap[3][3];
     bool tma_ok = false;
+    // ... of the fused pressure pass (box = one 64 x 32 tile plane; kernels_pressure_tma.cuh): [source][field][physical id]
+    // with source 0 = this slab, 1 / 2 = the lower / upper neighbour's peer-mapped arena; the stencil codes; the density
+    // [source][buffer]
+    CUtensorMap pmap[3][3][3];
+    CUtensorMap pmap_code;
+    CUtensorMap pmap_smoke[3][2];
+    bool pass_tma_ok = false, pass_tma_smoke_ok = false;
+    bool pass_tma_peer_ok[2] = {false, false};
 
     // host ranges this handle page-locked for the density readback (smk_register_host, or implicitly by smk_step)
     struct HostReg { char* p; size_t bytes; bool implicit; };
@@ -268,10 +283,12 @@ ObjP pack_objects(const smk_sim* s)
 void launch_codes(smk_sim* s)
 {
     const GridP& g = s->g;
+    const smk::TileFlags tf{s->cflag, s->cflag_tx, s->cflag_ty};
+    if (s->cflag) cudaMemsetAsync(s->cflag, 0, (size_t)g.nzc * s->cflag_tx * s->cflag_ty, s->stream);
     if ((g.W & 3) == 0)
-        smk::k_codes4<<<row_grid(g.cplane / 4, g.nzc), 256, 0, s->stream>>>(g, s->mask, s->code, g.zlo);
+        smk::k_codes4<<<row_grid(g.cplane / 4, g.nzc), 256, 0, s->stream>>>(g, s->mask, s->code, s->pcode, g.zlo, tf);
     else
-        smk::k_codes<<<row_grid(g.cplane, g.nzc), 256, 0, s->stream>>>(g, s->mask, s->code, g.zlo);
+        smk::k_codes<<<row_grid(g.cplane, g.nzc), 256, 0, s->stream>>>(g, s->mask, s->code, s->pcode, g.zlo, tf);
     count_launch(s, SMK_STAGE_FILL);
 }
 
@@ -540,17 +557,62 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
 {
     using C = smk::RegCfg<K, NW>;
     const GridP& g = s->g;
+    // SMK_PASS_KERNEL=reg | lean | tma selects the pass kernel for same-box A/B runs: the round-1 kernel
+    // (kernels_pressure_reg.cuh), its LDG-based rewrite (kernels_pressure_lean.cuh) or the TMA-staged kernel
+    // (kernels_pressure_tma.cuh, the default wherever its tensor maps exist)
+    static const char* kenv = getenv("SMK_PASS_KERNEL");
+    static const bool use_lean = kenv && strcmp(kenv, "lean") == 0;
+    bool use_tma = NW == 16 && s->pass_tma_ok && kenv && strcmp(kenv, "tma") == 0; // (work in progress: opt-in until it beats reg)
+    if (use_tma && s->pending_force && !s->pass_tma_smoke_ok) use_tma = false;
+    if (use_tma && from_peers && ((s->peer[0].arena && !s->pass_tma_peer_ok[0]) || (s->peer[1].arena && !s->pass_tma_peer_ok[1]))) use_tma = false;
     {
         int rc0;
         if ((rc0 = ensure_smem(s, smk::k_pressure_reg<K, NW, false>, C::SMEM)) || (rc0 = ensure_smem(s, smk::k_pressure_reg<K, NW, true>, C::SMEM)) ||
-            (rc0 = ensure_smem(s, smk::k_pressure_reg_bal<K, NW, false>, C::SMEM)) || (rc0 = ensure_smem(s, smk::k_pressure_reg_bal<K, NW, true>, C::SMEM)))
+            (rc0 = ensure_smem(s, smk::k_pressure_reg_bal<K, NW, false>, C::SMEM)) || (rc0 = ensure_smem(s, smk::k_pressure_reg_bal<K, NW, true>, C::SMEM)) ||
+            (rc0 = ensure_smem(s, smk::k_pressure_lean<K, NW, false, false>, C::SMEM)) || (rc0 = ensure_smem(s, smk::k_pressure_lean<K, NW, true, false>, C::SMEM)) ||
+            (rc0 = ensure_smem(s, smk::k_pressure_lean<K, NW, false, true>, C::SMEM)) || (rc0 = ensure_smem(s, smk::k_pressure_lean<K, NW, true, true>, C::SMEM)))
             return rc0;
     }
     // forcing + clamp deferred to this pass (exec_op / stage_pressure): the first pass of the step applies them on load
     const bool force = s->pending_force;
     s->pending_force = false;
-    auto kern = force ? smk::k_pressure_reg<K, NW, true> : smk::k_pressure_reg<K, NW, false>;
+    const bool maxw = s->want_maxw; // the last pass of a slab step also reduces max |w| (adaptive advection margin)
+    s->want_maxw = false;
     const smk::ForceArgs fa{s->smoke[s->now], s->pending_dt, s->gravity, s->alpha};
+    const int n = s->now;
+    auto launch_k = [&](dim3 grid, cudaStream_t st, int zchunk_, const smk::PassRange& r) {
+        if constexpr (NW == 16) {
+            if (use_tma) {
+                smk::PassMaps m;
+                const int id = s->vel_id[n];
+                for (int f = 0; f < 3; f++) { m.loc[f] = s->pmap[0][f][id]; m.lo[f] = s->pmap[1][f][id]; m.hi[f] = s->pmap[2][f][id]; }
+                m.pcode = s->pmap_code;
+                for (int src = 0; src < 3; src++) m.smoke[src] = s->pmap_smoke[src][n];
+                static const bool nocf = getenv("SMK_PASS_NO_CFLAG") != nullptr; // ablation: always the general variant
+                const unsigned char* cf = (K == 4 && !nocf && (int)grid.x == s->cflag_tx && (int)grid.y == s->cflag_ty) ? s->cflag : nullptr;
+                using T0 = smk::TmaCfg<K, 16, false>;
+                using T1 = smk::TmaCfg<K, 16, true>;
+                if (force) {
+                    auto k = maxw ? smk::k_pressure_tma<K, 16, true, true> : smk::k_pressure_tma<K, 16, true, false>;
+                    if (ensure_smem(s, k, T1::SMEM_END)) return;
+                    k<<<grid, T1::THREADS, T1::SMEM_END, st>>>(g, m, s->scratch[0], s->scratch[1], s->scratch[2], sweep0, zchunk_, r, fa, s->d_dyn, s->d_flags, cf);
+                } else {
+                    auto k = maxw ? smk::k_pressure_tma<K, 16, false, true> : smk::k_pressure_tma<K, 16, false, false>;
+                    if (ensure_smem(s, k, T0::SMEM_END)) return;
+                    k<<<grid, T0::THREADS, T0::SMEM_END, st>>>(g, m, s->scratch[0], s->scratch[1], s->scratch[2], sweep0, zchunk_, r, fa, s->d_dyn, s->d_flags, cf);
+                }
+                return;
+            }
+        }
+        if (use_lean) {
+            auto k = force ? (maxw ? smk::k_pressure_lean<K, NW, true, true> : smk::k_pressure_lean<K, NW, true, false>)
+                           : (maxw ? smk::k_pressure_lean<K, NW, false, true> : smk::k_pressure_lean<K, NW, false, false>);
+            k<<<grid, C::THREADS, C::SMEM, st>>>(g, s->scratch[0], s->scratch[1], s->scratch[2], s->pcode, sweep0, zchunk_, r, fa, s->d_dyn);
+        } else {
+            auto k = force ? smk::k_pressure_reg<K, NW, true> : smk::k_pressure_reg<K, NW, false>;
+            k<<<grid, C::THREADS, C::SMEM, st>>>(g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk_, r, fa);
+        }
+    };
     smk::PassRange pr{};
     pr.out_lo = out_lo; pr.out_hi = out_hi;
     pr.own_lo = g.zlo; pr.own_hi = g.zlo + g.nzn - 1; // default: everything stored counts as "own" (local source)
@@ -559,16 +621,20 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
                                plane0(s->w[s->now], g.nplane, g.zlo), g.zlo, plane0(s->smoke[s->now], g.cplane, g.zlo)};
     const int nz = out_hi - out_lo;
     const int tx = (g.W + 1 + C::OX - 1) / C::OX, ty = (g.SY + C::OY - 1) / C::OY;
-    const int zchunk = pick_zchunk(s, tx * ty, K, nz);
+    int zchunk = pick_zchunk(s, tx * ty, K, nz);
+    // the lean kernel addresses a chunk with 32-bit byte offsets: (planes of a chunk incl. lead-in) x plane bytes < 2^32
+    while ((long long)(zchunk + 2 * K + 2) * g.nplane * 4 >= (1ll << 32) && zchunk > 2 * K) zchunk = (zchunk + 1) / 2;
+    // Only the first and the last z-chunk may touch planes within K of the slab ends (the neighbours read those / they
+    // read the neighbours'): the LAST chunk must therefore hold at least K planes too (the others hold zchunk >= K)
+    while (from_peers && nz > zchunk && zchunk >= K && nz - (nz - 1) / zchunk * zchunk < K) zchunk++;
     const int nchunks = (nz + zchunk - 1) / zchunk;
-    const int n = s->now;
     static const bool overlap = getenv("SMK_P2P_NO_OVERLAP") == nullptr;
     if (from_peers) {
         pr.own_lo = s->geom.own_node_lo(); pr.own_hi = s->geom.own_node_hi();
         pr.lower = peer_planes(s, 0); pr.upper = peer_planes(s, 1);
     }
     static const bool inkernel = getenv("SMK_P2P_STREAM_SYNC") == nullptr;
-    if (from_peers && overlap && inkernel && nchunks >= 3 && zchunk >= K) {
+    if (from_peers && overlap && inkernel && nchunks >= 2 && zchunk >= K) {
         // One launch per pass, handshake inside the kernel (PassSync): the boundary chunks wait for the neighbour's
         // epoch themselves; the last boundary CTA per side publishes mine.  Only the first pass of a
         // step needs a signal from the stream: it must cover the advection and the fill in front of it.
@@ -617,8 +683,7 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
                 g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, pr, fa, ds->pieces,
                 ds->first);
         } else {
-            kern<<<dim3((unsigned)tx, (unsigned)ty, (unsigned)nchunks), C::THREADS, C::SMEM, s->stream>>>(
-                g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk, pr, fa);
+            launch_k(dim3((unsigned)tx, (unsigned)ty, (unsigned)nchunks), s->stream, zchunk, pr);
         }
     } else if (from_peers && overlap && nchunks >= 3 && zchunk >= K) {
         // The first and last z-chunk read neighbour planes; the interior chunks do not and never write planes a
@@ -641,13 +706,11 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
         if ((rc = peer_wait(s, s->aux_stream, sweep0 == 0 ? pre : pre - 1))) return rc;
         smk::PassRange pb = pr;
         pb.chunk_first = 0; pb.chunk_step = nchunks - 1;
-        kern<<<dim3((unsigned)tx, (unsigned)ty, 2u), C::THREADS, C::SMEM, s->aux_stream>>>(
-            g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk, pb, fa);
+        launch_k(dim3((unsigned)tx, (unsigned)ty, 2u), s->aux_stream, zchunk, pb);
         CK(s, cudaEventRecord(s->ev_join, s->aux_stream));
         smk::PassRange pi = pr;
         pi.chunk_first = 1; pi.chunk_step = 1;
-        kern<<<dim3((unsigned)tx, (unsigned)ty, (unsigned)(nchunks - 2)), C::THREADS, C::SMEM, s->stream>>>(
-            g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk, pi, fa);
+        launch_k(dim3((unsigned)tx, (unsigned)ty, (unsigned)(nchunks - 2)), s->stream, zchunk, pi);
         CK(s, cudaStreamWaitEvent(s->stream, s->ev_join, 0));
         s->launches++;
     } else {
@@ -674,8 +737,7 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
                 g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, pr, fa, ds->pieces,
                 ds->first);
         } else {
-            kern<<<dim3((unsigned)tx, (unsigned)ty, (unsigned)nchunks), C::THREADS, C::SMEM, s->stream>>>(
-                g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk, pr, fa);
+            launch_k(dim3((unsigned)tx, (unsigned)ty, (unsigned)nchunks), s->stream, zchunk, pr);
         }
     }
     swap_in_scratch(s);
@@ -1193,6 +1255,60 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+EncodeTiledFn encode_tiled_fn()
+{
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return (EncodeTiledFn)fn;
+}
+
+// tensor maps of the fused pressure pass over ONE arena (this slab's or a neighbour's): u, v, w [field][physical id] and
+// the two density buffers; box = 64 x 32 x 1 elements
+bool build_pass_maps(const GridP& g, char* arena, const ArenaLayout& lay, int nzn, int nzc, CUtensorMap (*node)[3], CUtensorMap* smoke, bool* smoke_ok)
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint32_t box[3] = {64, 32, 1};
+    const cuuint64_t ndims[3] = {(cuuint64_t)g.P, (cuuint64_t)g.SY, (cuuint64_t)nzn};
+    const cuuint64_t nstr[2] = {(cuuint64_t)g.P * 4, (cuuint64_t)g.nplane * 4};
+    for (int f = 0; f < 3; f++)
+        for (int id = 0; id < 3; id++) {
+            const size_t off = f == 0 ? lay.u[id] : f == 1 ? lay.v[id] : lay.w[id];
+            if (enc(&node[f][id], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, arena + off, ndims, nstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return false;
+        }
+    *smoke_ok = (g.W & 3) == 0 && nzc > 0;
+    const cuuint64_t cdims[3] = {(cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)std::max(nzc, 1)};
+    const cuuint64_t cstr[2] = {(cuuint64_t)g.W * 4, (cuuint64_t)g.cplane * 4};
+    for (int b = 0; b < 2; b++) {
+        if (*smoke_ok && enc(&smoke[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, arena + lay.smoke[b], cdims, cstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            *smoke_ok = false;
+        if (!*smoke_ok) smoke[b] = node[0][0]; // never dereferenced (forcing then runs as its own kernel)
+    }
+    return true;
+}
+
+bool build_pass_code_map(smk_sim* s)
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    const GridP& g = s->g;
+    if (!enc || g.nzc <= 0) return false;
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const cuuint32_t box[3] = {80, 32, 1};
+    const cuuint64_t dims[3] = {(cuuint64_t)g.PC, (cuuint64_t)g.H, (cuuint64_t)g.nzc};
+    const cuuint64_t str[2] = {(cuuint64_t)g.PC, (cuuint64_t)g.kplane};
+    return enc(&s->pmap_code, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, s->pcode, dims, str, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool build_tensor_maps(smk_sim* s)
 {
     void* fn = nullptr;
@@ -1282,7 +1398,19 @@ int create_common(smk_sim** out, unsigned W, unsigned H, unsigned D, int rank, i
     CKN(cudaMalloc(&s->d_flags, 64));
     CKN(cudaMemsetAsync(s->d_flags, 0, 64, s->stream));
     CKN(cudaMalloc(&s->code, code_count(g)));
+    CKN(cudaMalloc(&s->pcode, code_count(g)));
+    CKN(cudaMemsetAsync(s->pcode, 0, code_count(g), s->stream));
+    {
+        using T = smk::TmaCfg<4, 16, false>;
+        s->cflag_tx = ((int)W + 1 + T::OX - 1) / T::OX;
+        s->cflag_ty = ((int)H + 1 + T::OY - 1) / T::OY;
+        const size_t nb = std::max<size_t>(1, (size_t)g.nzc * s->cflag_tx * s->cflag_ty);
+        CKN(cudaMalloc(&s->cflag, nb));
+        CKN(cudaMemsetAsync(s->cflag, 1, nb, s->stream)); // until the first k_codes run: assume COMPLEX cells everywhere
+    }
     CKN(cudaMalloc(&s->d_scalar, 64));
+    CKN(cudaMalloc(&s->d_dyn, 64));
+    CKN(cudaMemsetAsync(s->d_dyn, 0, 64, s->stream));
     CKN(cudaMemsetAsync(s->code, 0, code_count(g), s->stream));
     // mask: fluid everywhere, solid on the plane y == 0 (cu:200-207)
     CKN(cudaMemsetAsync(s->mask, 1, mask_bytes, s->stream));
@@ -1291,6 +1419,11 @@ int create_common(smk_sim** out, unsigned W, unsigned H, unsigned D, int rank, i
         CKN(cudaMemcpyAsync(s->smoke[0], smoke0_full + (size_t)g.zlo * g.cplane, cb, cudaMemcpyHostToDevice, s->stream));
     CKN(cudaStreamSynchronize(s->stream));
     s->tma_ok = build_tensor_maps(s);
+    s->pass_tma_ok = build_pass_maps(g, s->arena, s->lay, g.nzn, g.nzc, s->pmap[0], s->pmap_smoke[0], &s->pass_tma_smoke_ok) && build_pass_code_map(s);
+    for (int side = 1; side <= 2; side++) { // placeholders until a neighbour is attached (never dereferenced)
+        memcpy(s->pmap[side], s->pmap[0], sizeof(s->pmap[0]));
+        memcpy(s->pmap_smoke[side], s->pmap_smoke[0], sizeof(s->pmap_smoke[0]));
+    }
 #undef CKN
     *out = s;
     return SMK_OK;
@@ -1405,7 +1538,7 @@ int smk_destroy(smk_sim* s)
         if (s->peer[i].arena && s->peer[i].ipc) cudaIpcCloseMemHandle(s->peer[i].arena);
     for (auto& d : s->schedules) { cudaFree(d.pieces); cudaFree(d.first); }
     cudaFree(s->arena);
-    cudaFree(s->mask); cudaFree(s->code); cudaFree(s->d_scalar); cudaFree(s->d_flags);
+    cudaFree(s->mask); cudaFree(s->code); cudaFree(s->pcode); cudaFree(s->cflag); cudaFree(s->d_scalar); cudaFree(s->d_flags); cudaFree(s->d_dyn);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     cudaGetLastError();
     delete s;
@@ -1680,6 +1813,13 @@ static int attach_common(smk_sim* s, int side, char* arena, bool ipc)
     pe.arena = arena; pe.ipc = ipc;
     pe.geom = slab::make_geom(s->geom.W, s->geom.H, s->geom.D, s->geom.world, s->geom.rank + (side == 0 ? -1 : 1), s->geom.ghost);
     pe.lay = make_layout(pe.geom);
+    {   // tensor maps over the neighbour's arena: the fused passes read its boundary planes by TMA over NVLink
+        GridP pg = s->g;
+        const int pnzc = pe.geom.zhc - pe.geom.zlo;
+        bool smoke_ok = false;
+        s->pass_tma_peer_ok[side] = build_pass_maps(pg, arena, pe.lay, pnzc + 1, pnzc, s->pmap[side + 1], s->pmap_smoke[side + 1], &smoke_ok) &&
+                                    (smoke_ok || !s->pass_tma_smoke_ok);
+    }
     s->p2p = (!s->geom.has_lower() || s->peer[0].arena) && (!s->geom.has_upper() || s->peer[1].arena);
     return SMK_OK;
 }
