@@ -220,6 +220,9 @@ int smk_stage_time(smk_sim* s, int stage, double* ms_total, long* launches);
 int smk_reset_timers(smk_sim* s);
 /* kernels launched by this handle since creation */
 long smk_launch_count(smk_sim* s);
+/* development aid (SMK_PASS_DEBUG=1 in the environment at smk_create): {start clock, cycles, SM id, variant * 1000 + planes}
+ * of every CTA of the most recent fused pressure pass; returns the number of CTAs written (0: not enabled) */
+int smk_debug_pass_ctas(smk_sim* s, long long* out4, int max_ctas);
 /* bytes the steps of this handle have copied device -> host so far (the density readback of cu:814; counted where the
  * copies are enqueued, so bench.py reports measured, not assumed, bytes per step) */
 unsigned long long smk_readback_bytes(smk_sim* s);

@@ -35,7 +35,7 @@
 #define TINY_INL __noinline__
 #endif
 #ifndef GEN_INL
-#define GEN_INL __noinline__
+#define GEN_INL __forceinline__
 #endif
 namespace smk {
 
@@ -53,7 +53,7 @@ struct TmaCfg {
     static constexpr unsigned RING_ABS = 0x20000u;             // shared-window address of the v ring (64 KB aligned)
     static constexpr unsigned RING_SLOT = 0x2000u, RING_MASK = 0xE000u; // 8 slots of 32 rows x 256 B: E[0..31] | O[0..31]
     static constexpr unsigned DUMMY_ABS = 0x30000u;            // 2 rows for the lanes of tile row LY-1 (no row above them)
-    static constexpr unsigned BAR_ABS = 0x30200u;              // NS mbarriers
+    static constexpr unsigned BAR_ABS = 0x30200u;              // NS mbarriers of the staging slots + the step barrier
     static constexpr unsigned SMEM_END = 0x30280u;
     static constexpr int THREADS = NW * 32;
     static_assert(NS * SLOT + 2048 <= (int)RING_ABS, "staging must fit below the v ring");
@@ -61,12 +61,24 @@ struct TmaCfg {
 
 // tensor maps of one launch: box = one tile plane.  Kernel parameter (__grid_constant__): the TMA unit reads them from there.
 struct PassMaps {
-    CUtensorMap loc[3];   // u, v, w of the slab's own "in" buffers                       box 64 x 32 x 1 floats
-    CUtensorMap lo[3];    // ... of the lower / upper neighbour (peer-mapped memory; unused copies of loc[] without one)
-    CUtensorMap hi[3];
+    // u, v, w of one source as ONE 4-D tensor (x, y, z, field): the three arrays of a buffer set lie a constant stride
+    // apart in the arena, so a single TMA instruction brings the plane of all three (box 64 x 32 x 1 x 3 floats).
+    // Measured with one instruction per array: the producer lane needed ~1550 cycles per z-step and the whole CTA
+    // waited for it.  src 0 = the slab's own "in" buffers, 1 / 2 = the lower / upper neighbour's (peer-mapped memory).
+    CUtensorMap uvw[3];
     CUtensorMap pcode;    // stencil codes (pcode)                                        box 80 x 32 x 1 bytes
     CUtensorMap smoke[3]; // density "now": own, lower neighbour's, upper neighbour's     box 64 x 32 x 1 floats
 };
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int x, int y, int z, int f, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(f), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
 
 // Packed pairs live in 64-bit registers from the moment they are loaded until they are stored: the f32x2 instructions
 // take .b64 operands, and every float2 <-> .b64 conversion in the source became a pair of register moves in the SASS of the
@@ -136,22 +148,36 @@ __device__ __forceinline__ bool mbar_wait1(unsigned long long* bar, unsigned par
 {
     unsigned ok = 0;
 #pragma unroll 1
-    for (int it = 0; it < (1 << 26) && !ok; it++)
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    for (int it = 0; it < (1 << 21) && !ok; it++)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(200000u) : "memory"); // suspend-time hint (ns): sleep, do not spin
     return ok != 0;
+}
+
+// Denormal-range quotients of "open" cells (acc = 6): the reciprocal + correction sequence can break a tie on the denormal
+// grid the wrong way for 0 < |d| < 2^-125; those lanes take the exact integer quotient (div6_tiny).  Inline and on the
+// QUOTIENT (one conversion to p afterwards): the decaying front of the SOR iteration is full of such values for the
+// first ticks of a scene, so this is not a cold path there.
+__device__ __forceinline__ b64 fix_tiny_q(b64 q, b64 d, unsigned ax, unsigned ay, bool six_lo = true, bool six_hi = true)
+{
+    float qx = lo32(q), qy = hi32(q);
+    if (six_lo && ax < 0x00ffffffu) qx = div6_tiny(lo32(d));
+    if (six_hi && ay < 0x00ffffffu) qy = div6_tiny(hi32(d));
+    return pk(qx, qy);
 }
 
 // ---- rare paths, out of line (they cost a call only where they are taken) ---------------------------------------------
 // denormal-range quotient of an "open" cell (acc = 6): the exact integer quotient, see div6_tiny
-__device__ TINY_INL b64 tiny_fix_pair(b64 d2, b64 P2)
+// ... and cells that are not updated (P = 0: old -/+ 0 = old).  act_lo / act_hi: the ACTIVE bits of the two cells.
+// six_lo / six_hi: the cell has six fluid neighbours (only the quotient by 6 can miss; see pressure_p_fast).
+__device__ __noinline__ b64 rare_fix_pair(b64 d2, b64 P2, unsigned act_lo, unsigned act_hi, unsigned six_lo, unsigned six_hi)
 {
     const float dx = lo32(d2), dy = hi32(d2);
     float px = lo32(P2), py = hi32(P2);
     const unsigned ax = (__float_as_uint(dx) & 0x7fffffffu) - 1u, ay = (__float_as_uint(dy) & 0x7fffffffu) - 1u;
-    if (ax < 0x00ffffffu) px = __double2float_rn(__dmul_rn((double)div6_tiny(dx), M19));
-    if (ay < 0x00ffffffu) py = __double2float_rn(__dmul_rn((double)div6_tiny(dy), M19));
-    return pk(px, py);
+    if (six_lo && ax < 0x00ffffffu) px = __double2float_rn(__dmul_rn((double)div6_tiny(dx), M19));
+    if (six_hi && ay < 0x00ffffffu) py = __double2float_rn(__dmul_rn((double)div6_tiny(dy), M19));
+    return pk(act_lo ? px : 0.f, act_hi ? py : 0.f);
 }
 // general update of a pair: per-cell neighbour count, per-face masks (a masked face gets its old value back).
 // cs: pcode of cell A in byte 0, of cell B in byte 2.  f = {U0, U1, V0, V1, W0, W1}, updated in place.
@@ -183,90 +209,80 @@ __device__ GEN_INL void general_update_pair(PairFaces& io, b64 d2, unsigned cs)
 __device__ __forceinline__ float2 f2(b64 v) { return make_float2(lo32(v), hi32(v)); }
 __device__ __forceinline__ b64 pk(float2 v) { return pk(v.x, v.y); }
 
-// rare fix-ups of the fast path, out of line: denormal-range quotients (exact integer quotient) and cells that are not
-// updated (P = 0: old -/+ 0 = old).  act_lo / act_hi: the ACTIVE bits of the two cells.
-__device__ __noinline__ b64 rare_fix_pair(b64 d2, b64 P2, unsigned act_lo, unsigned act_hi)
-{
-    const float dx = lo32(d2), dy = hi32(d2);
-    float px = lo32(P2), py = hi32(P2);
-    const unsigned ax = (__float_as_uint(dx) & 0x7fffffffu) - 1u, ay = (__float_as_uint(dy) & 0x7fffffffu) - 1u;
-    if (ax < 0x00ffffffu) px = __double2float_rn(__dmul_rn((double)div6_tiny(dx), M19));
-    if (ay < 0x00ffffffu) py = __double2float_rn(__dmul_rn((double)div6_tiny(dy), M19));
-    return pk(act_lo ? px : 0.f, act_hi ? py : 0.f);
-}
-
-// One sweep phase of one lane on ring position J (plane t-J): two same-colour cells of the lane's quad, in two parts.
+// One sweep phase of one lane on ring position J (plane t-J): two same-colour cells of the lane's quad.
 // PAR = x parity of the active colour (warp uniform).  a = shared address of this lane's E pair of the plane's row
 // (the parity offset is an immediate).  Pairs: E = (f[4h], f[4h+2]), O = (f[4h+1], f[4h+3]).
-//
-// Part A -- everything that does NOT depend on the previous sweep of the same z-step: the v faces, the u face of the
-// next quad, the stencil tests and four of the five additions of the divergence (cu:379-381 adds w1 LAST, and w1 = the
-// w0 of the sweep before is the only value two consecutive sweeps of a step share).  The step issues part A of sweep j+1
-// in front of part B of sweep j, in straight-line code: the independent loads, shuffles and adds fill the latency of
-// the serial chain (add, 3 x f32x2, F2F, DMUL, F2F, update w0) instead of queueing behind it.
-struct SweepA {
-    b64 V0, V1, U1, dA;
-    bool allact, simple;
-};
+// GENERAL = false: the CTA's planes hold no COMPLEX cell (flags written with the stencil codes, grid.h) -- the general
+// update is not even compiled in, so the hot path has no control-flow merge for the compiler to resolve with copies.
 template <int PAR, bool GENERAL>
-__device__ __forceinline__ SweepA sweep_a(const b64 ue, const b64 uo, const b64 we, const b64 wo, const unsigned a, const unsigned cw)
+__device__ __forceinline__ void tma_update(b64& ue, b64& uo, b64& we, b64& wo, b64& we1, b64& wo1, const unsigned a, const unsigned cw,
+                                           const bool hnz)
 {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr unsigned SH = 8u * PAR;                 // byte 0/2 (PAR 0) or 1/3 (PAR 1) of the code word
     constexpr unsigned M_AC = 0x00C000C0u << SH;      // ACTIVE | COMPLEX of both cells
     constexpr unsigned V_A = 0x00400040u << SH;       // ... == ACTIVE, not COMPLEX
     constexpr unsigned M_C = 0x00800080u << SH;
-    const b64 M1 = pk(-1.0f, -1.0f);
-    SweepA r;
-    r.V0 = lds64<PAR * 128>(a);
-    r.V1 = lds64<PAR * 128 + 256>(a);
-    const b64 U0 = PAR == 0 ? ue : uo, W0 = PAR == 0 ? we : wo;
-    r.U1 = PAR == 0 ? uo : pk(hi32(ue), __shfl_down_sync(FULL, lo32(ue), 1)); // PAR 1: u[4h+2], u[4h+4] (next quad's first face)
-    b64 d = ffma2(U0, M1, r.U1);         // -u0 + u1           (cu:379-381, left to right, one rounding each)
-    d = ffma2(r.V0, M1, d);              //  ... - v0
-    d = fadd2(d, r.V1);                  //  ... + v1
-    r.dA = ffma2(W0, M1, d);             //  ... - w0
-    // tier A: both cells of every lane ACTIVE with six fluid neighbours; tier B: no COMPLEX cell (some are not updated)
-    r.allact = __all_sync(FULL, (cw & M_AC) == V_A);
-    r.simple = !GENERAL || r.allact || __all_sync(FULL, (cw & (cw << 1) & M_C) == 0u);
-    return r;
-}
-template <int PAR, bool GENERAL>
-__device__ __forceinline__ void sweep_b(const SweepA& A, b64& ue, b64& uo, b64& we, b64& wo, b64& we1, b64& wo1, const unsigned a,
-                                        const unsigned cw, const bool hnz)
-{
-    constexpr unsigned FULL = 0xffffffffu;
-    constexpr unsigned SH = 8u * PAR;
     const b64 M1 = pk(-1.0f, -1.0f), R6 = pk(0x1.555556p-3f, 0x1.555556p-3f) /* RN(1/6) */, M6 = pk(-6.0f, -6.0f);
-    b64& U0r = PAR == 0 ? ue : uo;
-    b64& W0r = PAR == 0 ? we : wo;
-    b64& W1r = PAR == 0 ? we1 : wo1;
-    const b64 d = fadd2(A.dA, W1r);      //  ... + w1
-    b64 U1 = A.U1, V0 = A.V0, V1 = A.V1;
-    if (A.simple) {
+    b64 V0 = lds64<PAR * 128>(a), V1 = lds64<PAR * 128 + 256>(a);
+    b64 U0, U1, W0, W1;
+    if (PAR == 0) { U0 = ue; U1 = uo; W0 = we; W1 = we1; }
+    else {
+        U0 = uo; W0 = wo; W1 = wo1;
+        U1 = pk(hi32(ue), __shfl_down_sync(FULL, lo32(ue), 1)); // u[4h+2], u[4h+4] (next quad's first face)
+    }
+    b64 d = ffma2(U0, M1, U1);           // -u0 + u1           (cu:379-381, left to right, one rounding each)
+    d = ffma2(V0, M1, d);                //  ... - v0
+    d = fadd2(d, V1);                    //  ... + v1
+    d = ffma2(W0, M1, d);                //  ... - w0
+    d = fadd2(d, W1);                    //  ... + w1
+
+    // tier A: both cells of every lane ACTIVE with six fluid neighbours; tier B: no COMPLEX cell (some are not updated)
+    const bool allact = __all_sync(FULL, (cw & M_AC) == V_A);
+    if (!GENERAL || allact || __all_sync(FULL, (cw & (cw << 1) & M_C) == 0u)) {
         // q = d / 6 by reciprocal + one correction (exact for |d| >= 2^-125: exhaustive check)
         const b64 q0 = fmul2(d, R6);
         const b64 rem = ffma2(q0, M6, d);
-        const b64 q = ffma2(rem, R6, q0);
-        b64 P = p_from_q(q);
-        // below 2^-125 (and d != 0) a tie on the denormal grid can round the wrong way; cells that are not ACTIVE get
-        // P = 0: one branch for both rare cases
+        b64 q = ffma2(rem, R6, q0);
+        // below 2^-125 (and d != 0) a tie on the denormal grid can round the wrong way -> exact integer quotient
         const unsigned ax = (__float_as_uint(lo32(d)) & 0x7fffffffu) - 1u, ay = (__float_as_uint(hi32(d)) & 0x7fffffffu) - 1u;
-        if (__any_sync(FULL, min(ax, ay) < 0x00ffffffu) || !A.allact) P = rare_fix_pair(d, P, cw & (0x40u << SH), cw & (0x400000u << SH));
-        W0r = ffma2(P, M1, W0r);         // first: the next sweep of this step waits for it
-        W1r = fadd2(W1r, P);
+        if (__any_sync(FULL, min(ax, ay) < 0x00ffffffu)) q = fix_tiny_q(q, d, ax, ay);
+        b64 P = p_from_q(q);
+        if (!allact) // cells that are not ACTIVE get P = 0 (old -/+ 0 = old)
+            P = pk((cw & (0x40u << SH)) ? lo32(P) : 0.f, (cw & (0x400000u << SH)) ? hi32(P) : 0.f);
+        U0 = ffma2(P, M1, U0); U1 = fadd2(U1, P);
         V0 = ffma2(P, M1, V0); V1 = fadd2(V1, P);
-        U0r = ffma2(P, M1, U0r); U1 = fadd2(U1, P);
+        W0 = ffma2(P, M1, W0); W1 = fadd2(W1, P);
+    } else if (__all_sync(FULL, (((cw >> SH) & 0xC0u) != 0xC0u || ((cw >> SH) & 0x3Fu) == 0x3Bu) &&
+                                (((cw >> (SH + 16)) & 0xC0u) != 0xC0u || ((cw >> (SH + 16)) & 0x3Fu) == 0x3Bu))) {
+        // tier F: the only COMPLEX cells are cells standing on a solid one (every neighbour fluid but y-1) -- the row
+        // above the floor that every scene of the reference has (cu:200-207).  Same sequence with acc = 5 for those
+        // cells (exact for every input, see pressure_p_fast) and their lower v face left alone.
+        const bool fa_ = ((cw >> SH) & 0xC0u) == 0xC0u, fb_ = ((cw >> (SH + 16)) & 0xC0u) == 0xC0u;
+        const float r5 = 0x1.99999ap-3f, r6 = 0x1.555556p-3f;
+        const b64 RR2 = pk(fa_ ? r5 : r6, fb_ ? r5 : r6), MN = pk(fa_ ? -5.0f : -6.0f, fb_ ? -5.0f : -6.0f);
+        const b64 q0 = fmul2(d, RR2);
+        const b64 rem = ffma2(q0, MN, d);
+        b64 q = ffma2(rem, RR2, q0);
+        const unsigned ax = (__float_as_uint(lo32(d)) & 0x7fffffffu) - 1u, ay = (__float_as_uint(hi32(d)) & 0x7fffffffu) - 1u;
+        if (__any_sync(FULL, min(ax, ay) < 0x00ffffffu)) q = fix_tiny_q(q, d, ax, ay, !fa_, !fb_);
+        b64 P = p_from_q(q);
+        if (!allact) P = pk((cw & (0x40u << SH)) ? lo32(P) : 0.f, (cw & (0x400000u << SH)) ? hi32(P) : 0.f);
+        const b64 Pv0 = pk(fa_ ? 0.f : lo32(P), fb_ ? 0.f : hi32(P));
+        U0 = ffma2(P, M1, U0); U1 = fadd2(U1, P);
+        V0 = ffma2(Pv0, M1, V0); V1 = fadd2(V1, P);
+        W0 = ffma2(P, M1, W0); W1 = fadd2(W1, P);
     } else {
         PairFaces io;
-        io.f[0] = f2(U0r); io.f[1] = f2(U1); io.f[2] = f2(V0); io.f[3] = f2(V1); io.f[4] = f2(W0r); io.f[5] = f2(W1r);
+        io.f[0] = f2(U0); io.f[1] = f2(U1); io.f[2] = f2(V0); io.f[3] = f2(V1); io.f[4] = f2(W0); io.f[5] = f2(W1);
         general_update_pair(io, d, cw >> SH);
-        U0r = pk(io.f[0]); U1 = pk(io.f[1]); V0 = pk(io.f[2]); V1 = pk(io.f[3]); W0r = pk(io.f[4]); W1r = pk(io.f[5]);
+        U0 = pk(io.f[0]); U1 = pk(io.f[1]); V0 = pk(io.f[2]); V1 = pk(io.f[3]); W0 = pk(io.f[4]); W1 = pk(io.f[5]);
     }
     sts64<PAR * 128>(a, V0);
     sts64<PAR * 128 + 256>(a, V1);
-    if (PAR == 0) uo = U1;
+    if (PAR == 0) { ue = U0; uo = U1; we = W0; we1 = W1; }
     else {
+        uo = U0; wo = W0; wo1 = W1;
         const float from_left = __shfl_up_sync(FULL, hi32(U1), 1); // the left quad's updated u[4h]
         ue = pk(hnz ? from_left : lo32(ue), lo32(U1));              // h == 0: tile edge, face stays stale (halo)
     }
@@ -278,16 +294,56 @@ __device__ __forceinline__ void force_clamp_node_pc(float& u, float& v, float& w
     force_clamp_node(u, v, w, ((pc & 0xC0u) ? CODE_SELF : 0u) | (pc & CODE_SY0), d, clampable, fa);
 }
 
+// TMA producer, out of line (one lane of warp 0 calls it once per z-step): plane z of its source into a staging slot.
+struct IssueArgs {
+    const PassMaps* maps;
+    unsigned long long* bars;
+    unsigned char* stage;
+    int x0, y0, x0k, zlo, own_lo, own_hi, lo_zlo, hi_zlo;
+    bool has_lo, has_hi;
+    long long* trace; // development aid
+    int t0;
+};
+template <int K, int NW, bool FORCE>
+__device__ __forceinline__ void tma_issue_plane(const IssueArgs& q, int z, int slot)
+{
+    using C = TmaCfg<K, NW, FORCE>;
+    int src = 0, zr = z - q.zlo;
+    if (q.has_lo && z < q.own_lo) { src = 1; zr = z - q.lo_zlo; }
+    else if (q.has_hi && z > q.own_hi) { src = 2; zr = z - q.hi_zlo; }
+    const CUtensorMap* ms = &q.maps->smoke[src];
+    unsigned char* dst = q.stage + slot * C::SLOT;
+    long long* tr = (q.trace && z - q.t0 < 80 && z >= q.t0) ? q.trace + 16 * 80 * 8 + (z - q.t0) * 8 : nullptr;
+    if (tr) tr[0] = clock64();
+    mbar_expect_tx(&q.bars[slot], 3u * C::FB + (unsigned)(C::KW * C::LY) + (FORCE ? (unsigned)C::FB : 0u));
+    if (tr) tr[1] = clock64();
+    tma_load_4d(dst, &q.maps->uvw[src], q.x0, q.y0, zr, 0, &q.bars[slot]);
+    if (tr) tr[2] = clock64();
+    tma_load_3d(dst + 3 * C::FB, &q.maps->pcode, q.x0k, q.y0, z - q.zlo, &q.bars[slot]);
+    if (tr) tr[3] = clock64();
+    if (FORCE) tma_load_3d(dst + 3 * C::FB + C::KB, ms, q.x0, q.y0, zr, &q.bars[slot]);
+}
+
 // One PIECE of a pass: the tile (bx, by) marched over the output node planes [zo0, zo1) (K lead-in planes below, K - 1
 // above).  MAXW: also reduce max |w| over the planes written (bound of the next advection's backtrace in z).
+//
+// Step t:  (a) write out v of plane t-K-1;  (b) ENTER plane t+1 -- wait for its staged copy, registers + v ring;
+//          (c) K sweeps on planes t-1 .. t-K;  (d) write out u, w of plane t-K;  (e) barrier.
+// (b) sits in front of (c) in program order but nothing in (c) depends on it (plane t+1 is first touched by sweep 1 of
+// step t+1, as the w above plane t): its mbarrier probe, its four LDS and its v stores drain while the sweeps run, and a
+// warp that leaves the barrier finds everything the next sweeps need in registers and shared memory.
+// The register ring has K+2 entries; plane p lives in entry (p - t0 + c) mod (K+2) for its whole life, and the loop is
+// unrolled over the K+2 rotations (no ring shift; round 1 moved 36 registers per step).  K+2 is even, so the rotation
+// also fixes the x parity of the active colour (c = parity of the warp's first step selects where it enters the pattern).
 template <int K, int NW, bool FORCE, bool MAXW, bool GENERAL>
 __device__ __forceinline__ void tma_pass_piece(const GridP& g, const PassMaps& maps, float* __restrict__ uo, float* __restrict__ vo,
                                                float* __restrict__ wo, int sweep0, const PassRange& pr, const ForceArgs& fa,
                                                unsigned char* __restrict__ smem, int bx, int by, int zo0, int zo1,
-                                               unsigned* __restrict__ wmax, int* __restrict__ flags)
+                                               unsigned* __restrict__ wmax, int* __restrict__ flags, long long* __restrict__ trace = nullptr)
 {
     using C = TmaCfg<K, NW, FORCE>;
-    constexpr int LY = C::LY, R = K + 1, NS = C::NS;
+    constexpr int LY = C::LY, RR = K + 2, NS = C::NS;
+    static_assert(RR % 2 == 0, "the unrolled pattern fixes the colour parity per rotation");
     // (the warp index through a shuffle: the compiler then knows that everything derived from it is warp-uniform and
     // emits plain uniform branches around the sweeps instead of divergence bookkeeping)
     const int lane = threadIdx.x & 31, wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -295,7 +351,8 @@ __device__ __forceinline__ void tma_pass_piece(const GridP& g, const PassMaps& m
     // rows of a warp and the deepest sweep they need: kernels_pressure_reg.cuh (trapezoid halo, shallow rows paired)
     constexpr bool SKIP = (K == 4 && NW >= 8 && NW % 4 == 0);
     const int hb = lane >> 4;
-    const int yl = !SKIP ? wid + hb * NW : wid >= 4 ? wid + hb * ((LY - 8) / 2) : hb == 0 ? wid : wid == 3 ? LY - 1 : LY - 2 - wid;
+    const int widr = wid;
+    const int yl = !SKIP ? widr + hb * NW : widr >= 4 ? widr + hb * ((LY - 8) / 2) : hb == 0 ? widr : widr == 3 ? LY - 1 : LY - 2 - widr;
     const int jmax = (SKIP && wid < 3) ? wid + 1 : K;
     const int x0 = bx * C::OX - C::HX;
     const int y0 = by * C::OY - K;
@@ -319,34 +376,26 @@ __device__ __forceinline__ void tma_pass_piece(const GridP& g, const PassMaps& m
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < NS; i++) mbar_init(&bars[i], 1);
+        mbar_init(&bars[NS], C::THREADS); // the step barrier
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // TMA producer (thread 0): plane z of the current source into staging slot `slot`
-    const bool has_lo = pr.lower.u != nullptr, has_hi = pr.upper.u != nullptr;
-    auto issue = [&](int z, int slot) {
-        const CUtensorMap* m = maps.loc;
-        const CUtensorMap* ms = &maps.smoke[0];
-        int zr = z - g.zlo;
-        if (has_lo && z < pr.own_lo) { m = maps.lo; ms = &maps.smoke[1]; zr = z - pr.lower.zlo; }
-        else if (has_hi && z > pr.own_hi) { m = maps.hi; ms = &maps.smoke[2]; zr = z - pr.upper.zlo; }
-        unsigned char* dst = stage + slot * C::SLOT;
-        mbar_expect_tx(&bars[slot], 3u * C::FB + (unsigned)(C::KW * LY) + (FORCE ? (unsigned)C::FB : 0u));
-        tma_load_3d(dst, &m[0], x0, y0, zr, &bars[slot]);
-        tma_load_3d(dst + C::FB, &m[1], x0, y0, zr, &bars[slot]);
-        tma_load_3d(dst + 2 * C::FB, &m[2], x0, y0, zr, &bars[slot]);
-        tma_load_3d(dst + 3 * C::FB, &maps.pcode, x0k, y0, z - g.zlo, &bars[slot]);
-        if (FORCE) tma_load_3d(dst + 3 * C::FB + C::KB, ms, x0, y0, zr, &bars[slot]);
-    };
-    if (threadIdx.x == 0)
-        for (int i = 0; i < NS - 1 && t0 + i <= t1; i++) issue(t0 + i, i);
+    const IssueArgs iq{&maps, bars, stage, x0, y0, x0k, g.zlo, pr.own_lo, pr.own_hi, pr.lower.zlo, pr.upper.zlo,
+                       pr.lower.u != nullptr, pr.upper.u != nullptr, trace, t0};
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&maps.uvw[0]); tma_prefetch_desc(&maps.pcode);
+        if (iq.has_lo) tma_prefetch_desc(&maps.uvw[1]);
+        if (iq.has_hi) tma_prefetch_desc(&maps.uvw[2]);
+        if (FORCE) tma_prefetch_desc(&maps.smoke[0]);
+        for (int i = 0; i < NS && t0 + i <= t1; i++) tma_issue_plane<K, NW, FORCE>(iq, t0 + i, i);
+    }
 
-    // register ring, index k = plane t-k
-    b64 UE[R], UO[R], WE[R], WO[R];
-    unsigned CW[R];
+    // register ring
+    b64 UE[RR], UO[RR], WE[RR], WO[RR];
+    unsigned CW[RR];
 #pragma unroll
-    for (int k = 0; k < R; k++) {
+    for (int k = 0; k < RR; k++) {
         UE[k] = UO[k] = WE[k] = WO[k] = 0ull;
         CW[k] = 0;
     }
@@ -367,31 +416,13 @@ __device__ __forceinline__ void tma_pass_piece(const GridP& g, const PassMaps& m
     float wm = 0.f;
 
     unsigned tt = 0;            // (t - t0) << 13: slot bits of plane t in the v ring (masked)
-    int ss = 0;                 // staging slot of plane t
+    int ss = 0;                 // staging slot of plane t+1 (the plane that enters during step t)
     unsigned ph = 0;            // parity bits of the NS mbarriers (bit i flips every time slot i is consumed)
     int t = t0;
     bool failed = false;
 
-    // One z-step.  ROT = (t - t0) mod R and PAR = x parity of the active colour are COMPILE-TIME: plane p lives in the
-    // physical ring entry p mod R for its whole life (position k of step t is entry (ROT - k) mod R), so the ring is never
-    // shifted -- the loop below is unrolled over the 2R combinations instead (round 1 moved 36 registers per step).
-    // Returns false when the piece is finished (or a TMA transaction was lost).
-    auto step = [&](auto rot_c, auto par_c) -> bool {
-        constexpr int ROT = decltype(rot_c)::value, PAR = decltype(par_c)::value;
-        auto ph_of = [](int k) { return ((ROT - k) % R + R) % R; };
-        // (a) v of plane t-K-1 became final with the previous step (behind its barrier): write it out
-        {
-            const int s2 = t - K - 1;
-            if (s2 >= zo0 && s2 < zo1 && sok) {
-                const unsigned a = C::RING_ABS + ((tt - (unsigned)(K + 1) * C::RING_SLOT) & C::RING_MASK) + lq;
-                const b64 ve = lds64<0>(a), vq = lds64<128>(a);
-                *reinterpret_cast<float4*>(pov) = make_float4(lo32(ve), lo32(vq), hi32(ve), hi32(vq));
-            }
-        }
-        if (t > t1) return false;
-        // (b) plane t enters: wait for its staged copy; u, w and the code word go to ring position 0, v to the v ring.
-        //     The producer is a lane of warp 0, whose rows need one sweep per step instead of K: it has the time.
-        if (threadIdx.x == 0 && t + NS - 1 <= t1) issue(t + NS - 1, ss == 0 ? NS - 1 : ss - 1); // the slot plane t-1 just left
+    // enter plane z (staged in slot ss, v-ring slot bits vt) into the ring entry E
+    auto enter = [&](b64& ue, b64& uq, b64& we, b64& wq, unsigned& cw, int z, unsigned vt) -> bool {
         if (!mbar_wait1(&bars[ss], (ph >> ss) & 1u)) { flags[2] = 1; failed = true; return false; }
         ph ^= 1u << ss;
         float4 pu = *reinterpret_cast<const float4*>(lst + ss * C::SLOT);
@@ -400,38 +431,84 @@ __device__ __forceinline__ void tma_pass_piece(const GridP& g, const PassMaps& m
         unsigned pc = *reinterpret_cast<const unsigned*>(lkc + ss * C::SLOT);
         if (FORCE) { // first pass of the step: forcing + clamp on the way in
             const float4 pd = *reinterpret_cast<const float4*>(lst + ss * C::SLOT + 3 * C::FB + C::KB);
-            const bool cl = yg >= 1 && yg < g.H && t >= 1 && t < g.D; // + 1 <= x < W per node
+            const bool cl = yg >= 1 && yg < g.H && z >= 1 && z < g.D; // + 1 <= x < W per node
             force_clamp_node_pc(pu.x, pv.x, pw.x, pc & 255u, pd.x, cl && xg >= 1 && xg < g.W, fa);
             force_clamp_node_pc(pu.y, pv.y, pw.y, (pc >> 8) & 255u, pd.y, cl && xg + 1 < g.W, fa);
             force_clamp_node_pc(pu.z, pv.z, pw.z, (pc >> 16) & 255u, pd.z, cl && xg + 2 < g.W, fa);
             force_clamp_node_pc(pu.w, pv.w, pw.w, pc >> 24, pd.w, cl && xg + 3 < g.W, fa);
         }
-        UE[ph_of(0)] = pk(pu.x, pu.z); UO[ph_of(0)] = pk(pu.y, pu.w);
-        WE[ph_of(0)] = pk(pw.x, pw.z); WO[ph_of(0)] = pk(pw.y, pw.w);
-        CW[ph_of(0)] = pc;
-        {
-            const unsigned a = C::RING_ABS + (tt & C::RING_MASK) + lq;
-            sts32<0>(a, pv.x); sts32<4>(a, pv.z); sts32<128>(a, pv.y); sts32<132>(a, pv.w);
+        ue = pk(pu.x, pu.z); uq = pk(pu.y, pu.w);
+        we = pk(pw.x, pw.z); wq = pk(pw.y, pw.w);
+        cw = pc;
+        const unsigned a = C::RING_ABS + (vt & C::RING_MASK) + lq;
+        sts32<0>(a, pv.x); sts32<4>(a, pv.z); sts32<128>(a, pv.y); sts32<132>(a, pv.w);
+        if (++ss == NS) ss = 0;
+        return true;
+    };
+
+    // Split-phase step barrier (an mbarrier every thread arrives on): a thread ARRIVES right after its last v store of a
+    // step and WAITS just before the first sweep of the next one.  What lies in between -- writing out u and w, the
+    // producer's TMA issue, entering the next plane -- overlaps the skew between the warps instead of following it.
+    // development aid: timestamps of three warps of one CTA (tools/cta_times.py trace)
+#define TRACE(k)                                                                                              \
+    do {                                                                                                      \
+        if (trace && lane == 0 && (t - t0) < 80) trace[((wid * 80) + (t - t0)) * 8 + (k)] = clock64();         \
+    } while (0)
+    unsigned long long* const sbar = bars + NS;
+    unsigned sph = 0;
+    auto step_arrive = [&]() { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sbar)) : "memory"); };
+    auto step_wait = [&]() -> bool {
+        if (!mbar_wait1(sbar, sph)) { flags[2] = 1; failed = true; return false; }
+        sph ^= 1u;
+        return true;
+    };
+
+    // One z-step at rotation ROT (compile time): position k (plane t-k, k = -1 .. K) is ring entry (ROT - k) mod RR, and
+    // the colour parity of the step is ROT & 1.  Returns false when the piece is finished (or a TMA transaction was lost).
+    auto step = [&](auto rot_c) -> bool {
+        constexpr int ROT = decltype(rot_c)::value, PAR = ROT & 1;
+        auto ph_of = [](int k) { return ((ROT - k) % RR + RR) % RR; };
+        // every row has finished the sweeps of step t-1 (and entered plane t)
+        if (!step_wait()) return false;
+        TRACE(3);
+        if (t > t1) { // only the last plane's v is left to write
+            const int s2 = t - K - 1;
+            if (s2 >= zo0 && s2 < zo1 && sok) {
+                const unsigned a = C::RING_ABS + ((tt - (unsigned)(K + 1) * C::RING_SLOT) & C::RING_MASK) + lq;
+                const b64 ve = lds64<0>(a), vq = lds64<128>(a);
+                *reinterpret_cast<float4*>(pov) = make_float4(lo32(ve), lo32(vq), hi32(ve), hi32(vq));
+            }
+            return false;
         }
+        // Plane t-1 was entered during step t-2, in front of every thread's arrive of step t-1: its staging slot has been
+        // read by everyone and is refilled now.  The producer is a lane of warp 0, whose rows need one sweep per step
+        // instead of K: it has the time.
+        if (threadIdx.x == 0 && t > t0 && t - 1 + NS <= t1) tma_issue_plane<K, NW, FORCE>(iq, t - 1 + NS, (ss + NS - 2) % NS);
+        TRACE(0);
         // (c) sweep j runs on cell plane t-j with colour (sweep0+j-1)&1: the active x parity of a row,
         //     (y + (t-j) + sweep0 + j - 1) & 1 = (y + t + sweep0 + 1) & 1, is the same for all K sweeps of this step.
-        //     No barrier between the sweeps: they touch different planes of v, and u / w are private to the lane.
-        //     ALL K sweeps run in every step and on every row: the ones the trapezoid halo does not need (sweep j of a
-        //     plane less than j-1 above t0, or of a row closer than j to the tile edge) only ever feed values that are
-        //     not needed either -- which is why round 1 could skip them; here they buy straight-line code, and the warps
-        //     they would have spared wait at the step's barrier anyway.
-        {
-            auto adr = [&](int j) { return ((tt - (unsigned)j * C::RING_SLOT) & sw_mask) | sw_base; };
-            SweepA A = sweep_a<PAR, GENERAL>(UE[ph_of(1)], UO[ph_of(1)], WE[ph_of(1)], WO[ph_of(1)], adr(1), CW[ph_of(1)]);
+        //     Plane t-j needs sweep j only if it lies j-1 planes above t0 (t - 2j + 1 >= t0) and the warp's rows need
+        //     it (j <= jmax): one sweep count per step.  No barrier between the sweeps: they touch different planes
+        //     of v, and u / w are private to the lane.
+        const int nsw = min(jmax, (t - t0 + 1) >> 1);
 #pragma unroll
-            for (int j = 1; j <= K; j++) {
-                SweepA An = A;
-                if (j < K) An = sweep_a<PAR, GENERAL>(UE[ph_of(j + 1)], UO[ph_of(j + 1)], WE[ph_of(j + 1)], WO[ph_of(j + 1)], adr(j + 1), CW[ph_of(j + 1)]);
-                sweep_b<PAR, GENERAL>(A, UE[ph_of(j)], UO[ph_of(j)], WE[ph_of(j)], WO[ph_of(j)], WE[ph_of(j - 1)], WO[ph_of(j - 1)], adr(j),
-                                      CW[ph_of(j)], hnz);
-                A = An;
+        for (int j = 1; j <= K; j++) {
+            if (j <= nsw)
+                tma_update<PAR, GENERAL>(UE[ph_of(j)], UO[ph_of(j)], WE[ph_of(j)], WO[ph_of(j)], WE[ph_of(j - 1)], WO[ph_of(j - 1)],
+                                         ((tt - (unsigned)j * C::RING_SLOT) & sw_mask) | sw_base, CW[ph_of(j)], hnz);
+            TRACE(3 + j);
+            if (j == 1) { // (a) v of plane t-K-1 became final with the previous step: write it out (off the critical path)
+                const int s2 = t - K - 1;
+                if (s2 >= zo0 && s2 < zo1 && sok) {
+                    const unsigned a = C::RING_ABS + ((tt - (unsigned)(K + 1) * C::RING_SLOT) & C::RING_MASK) + lq;
+                    const b64 ve = lds64<0>(a), vq = lds64<128>(a);
+                    *reinterpret_cast<float4*>(pov) = make_float4(lo32(ve), lo32(vq), hi32(ve), hi32(vq));
+                }
             }
         }
+        // (e) this thread's v faces of step t are written
+        TRACE(1);
+        step_arrive();
         // (d) u and w of plane t-K are final and private to this lane: write them out now
         {
             const int s = t - K;
@@ -443,47 +520,36 @@ __device__ __forceinline__ void tma_pass_piece(const GridP& g, const PassMaps& m
             }
             pou += g.nplane; pow_ += g.nplane; pov += g.nplane;
         }
-        // (f) v faces written in this step are read by other rows in the next one; the staged copy of plane t is free
-        __syncthreads();
+        // (b) plane t+1 enters (its staging slot was filled NS-1 steps ago): registers + v ring.  Its v stores are
+        //     ordered before this thread's NEXT arrive, which is what the rows that read them (step t+2) wait for.
+        if (t + 1 <= t1) {
+            if (!enter(UE[ph_of(-1)], UO[ph_of(-1)], WE[ph_of(-1)], WO[ph_of(-1)], CW[ph_of(-1)], t + 1, tt + C::RING_SLOT)) return false;
+        }
+        TRACE(2);
         tt += C::RING_SLOT;
-        if (++ss == NS) ss = 0;
         t++;
         return true;
     };
-    // unrolled over ring rotation x parity: step s of the pattern has ROT = s mod R, PAR = (s + c) & 1 with
-    // c = parity of this warp's first step.  A warp with c = 1 enters the pattern at s = R (same rotation, other parity).
-    static_assert(R % 2 == 1, "the 2R pattern needs an odd ring depth");
-    bool second_half_only = ((rowpar + t0) & 1) != 0;
-    if (GENERAL) { // the rare CTAs with COMPLEX cells: compact code -- one step per iteration, ring shifted by register moves
-        for (;;) {
-            const bool go = ((rowpar + t) & 1) ? step(std::integral_constant<int, 0>{}, std::integral_constant<int, 1>{})
-                                               : step(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
-            if (!go) break;
-            // position k of the next step = position k-1 of this one; with ROT = 0 position k is entry (R - k) % R
-#pragma unroll
-            for (int k = K; k >= 1; k--) {
-                const int to = (R - k) % R, from = (R - (k - 1)) % R;
-                UE[to] = UE[from]; UO[to] = UO[from]; WE[to] = WE[from]; WO[to] = WO[from]; CW[to] = CW[from];
-            }
-        }
-    } else
+
+    // prologue: plane t0 enters position 0 of the first step, i.e. ring entry c
+    const bool c1 = ((rowpar + t0) & 1) != 0;
+    {
+        bool ok;
+        if (c1) ok = enter(UE[1], UO[1], WE[1], WO[1], CW[1], t0, 0u);
+        else ok = enter(UE[0], UO[0], WE[0], WO[0], CW[0], t0, 0u);
+        if (!ok) return;
+        step_arrive();   // plane t0 is in: counts as "step t0 - 1 done" for the first wait
+    }
+    bool skip0 = c1;
     for (;;) {
-        if (!second_half_only) {
-            if (!step(std::integral_constant<int, 0 % R>{}, std::integral_constant<int, 0>{})) break;
-            if (!step(std::integral_constant<int, 1 % R>{}, std::integral_constant<int, 1>{})) break;
-            if (!step(std::integral_constant<int, 2 % R>{}, std::integral_constant<int, 0>{})) break;
-            if (R > 3) {
-                if (!step(std::integral_constant<int, 3 % R>{}, std::integral_constant<int, 1>{})) break;
-                if (!step(std::integral_constant<int, 4 % R>{}, std::integral_constant<int, 0>{})) break;
-            }
-        }
-        second_half_only = false;
-        if (!step(std::integral_constant<int, 0 % R>{}, std::integral_constant<int, 1>{})) break;
-        if (!step(std::integral_constant<int, 1 % R>{}, std::integral_constant<int, 0>{})) break;
-        if (!step(std::integral_constant<int, 2 % R>{}, std::integral_constant<int, 1>{})) break;
-        if (R > 3) {
-            if (!step(std::integral_constant<int, 3 % R>{}, std::integral_constant<int, 0>{})) break;
-            if (!step(std::integral_constant<int, 4 % R>{}, std::integral_constant<int, 1>{})) break;
+        if (!skip0) { if (!step(std::integral_constant<int, 0>{})) break; }
+        skip0 = false;
+        if (!step(std::integral_constant<int, 1>{})) break;
+        if (!step(std::integral_constant<int, 2 % RR>{})) break;
+        if (!step(std::integral_constant<int, 3 % RR>{})) break;
+        if (RR > 4) {
+            if (!step(std::integral_constant<int, 4 % RR>{})) break;
+            if (!step(std::integral_constant<int, 5 % RR>{})) break;
         }
     }
     if (failed) return;
@@ -497,8 +563,9 @@ template <int K, int NW, bool FORCE, bool MAXW>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_pressure_tma(GridP g, const __grid_constant__ PassMaps maps, float* __restrict__ uo, float* __restrict__ vo, float* __restrict__ wo,
                int sweep0, int zchunk, PassRange pr, ForceArgs fa, unsigned* __restrict__ wmax, int* __restrict__ flags,
-               const unsigned char* __restrict__ cflag)
+               const unsigned char* __restrict__ cflag, long long* __restrict__ dbg)
 {
+    const long long dbg_t0 = dbg ? clock64() : 0;
     static_assert(K % 2 == 0 && NW % 2 == 0, "a pass is whole red+black pairs; both rows of a warp share the parity");
     using C = TmaCfg<K, NW, FORCE>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -543,8 +610,16 @@ k_pressure_tma(GridP g, const __grid_constant__ PassMaps maps, float* __restrict
             for (int z = za + (int)threadIdx.x; z <= zb; z += (int)blockDim.x) cx |= cflag[(long long)(z - g.zlo) * per + me];
             cx = __syncthreads_or(cx);
         }
-        if (cx) tma_pass_piece<K, NW, FORCE, MAXW, true>(g, maps, uo, vo, wo, sweep0, pr, fa, smem_raw, (int)blockIdx.x, (int)blockIdx.y, zo0, zo1, wmax, flags);
-        else tma_pass_piece<K, NW, FORCE, MAXW, false>(g, maps, uo, vo, wo, sweep0, pr, fa, smem_raw, (int)blockIdx.x, (int)blockIdx.y, zo0, zo1, wmax, flags);
+        if (cx) tma_pass_piece<K, NW, FORCE, MAXW, true>(g, maps, uo, vo, wo, sweep0, pr, fa, smem_raw, (int)blockIdx.x, (int)blockIdx.y, zo0, zo1, wmax, flags,
+                                                         (dbg && blockIdx.x == dbg[(1 << 17) - 3] && blockIdx.y == dbg[(1 << 17) - 2] && blockIdx.z == dbg[(1 << 17) - 1]) ? dbg + (1 << 17) : nullptr);
+        else tma_pass_piece<K, NW, FORCE, MAXW, false>(g, maps, uo, vo, wo, sweep0, pr, fa, smem_raw, (int)blockIdx.x, (int)blockIdx.y, zo0, zo1, wmax, flags,
+                                                       (dbg && blockIdx.x == dbg[(1 << 17) - 3] && blockIdx.y == dbg[(1 << 17) - 2] && blockIdx.z == dbg[(1 << 17) - 1]) ? dbg + (1 << 17) : nullptr);
+        if (dbg && threadIdx.x == 0) { // development aid (SMK_PASS_DEBUG): per-CTA start, duration, SM and variant
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            long long* o = dbg + 4 * ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+            o[0] = dbg_t0; o[1] = clock64() - dbg_t0; o[2] = smid; o[3] = cx * 1000 + (zo1 - zo0);
+        }
     }
     if (bside >= 0) { // the last boundary CTA of this side publishes the epoch
         __threadfence();

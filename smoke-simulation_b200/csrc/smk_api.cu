@@ -91,6 +91,8 @@ struct smk_sim {
     int solver = SMK_SOLVER_RBGS;
     int pass_epoch_next = -1;   // half-sweep index whose handshake epoch the previous pass kernel publishes itself
     bool want_maxw = false;     // the next fused pass also reduces max |w| over the planes it writes into d_dyn[0]
+    long long* d_passdbg = nullptr; // SMK_PASS_DEBUG=1: {start clock, cycles, SM id, variant} of every CTA of the last fused pass
+    int passdbg_ctas = 0;
     unsigned* d_dyn = nullptr;  // device words: [0] max |w| bits (atomicMax), [1] advection margin in planes
     bool pending_force = false; // forcing + clamp of this step are applied by the first pressure pass (fused)
     float pending_dt = 0.f;
@@ -133,7 +135,7 @@ struct smk_sim {
     // ... of the fused pressure pass (box = one 64 x 32 tile plane; kernels_pressure_tma.cuh): [source][field][physical id]
     // with source 0 = this slab, 1 / 2 = the lower / upper neighbour's peer-mapped arena; the stencil codes; the density
     // [source][buffer]
-    CUtensorMap pmap[3][3][3];
+    CUtensorMap pmap[3][3];   // [source][physical id]: u, v, w as one 4-D tensor (x, y, z, field)
     CUtensorMap pmap_code;
     CUtensorMap pmap_smoke[3][2];
     bool pass_tma_ok = false, pass_tma_smoke_ok = false;
@@ -585,7 +587,7 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
             if (use_tma) {
                 smk::PassMaps m;
                 const int id = s->vel_id[n];
-                for (int f = 0; f < 3; f++) { m.loc[f] = s->pmap[0][f][id]; m.lo[f] = s->pmap[1][f][id]; m.hi[f] = s->pmap[2][f][id]; }
+                for (int src = 0; src < 3; src++) m.uvw[src] = s->pmap[src][id];
                 m.pcode = s->pmap_code;
                 for (int src = 0; src < 3; src++) m.smoke[src] = s->pmap_smoke[src][n];
                 static const bool nocf = getenv("SMK_PASS_NO_CFLAG") != nullptr; // ablation: always the general variant
@@ -595,12 +597,13 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
                 if (force) {
                     auto k = maxw ? smk::k_pressure_tma<K, 16, true, true> : smk::k_pressure_tma<K, 16, true, false>;
                     if (ensure_smem(s, k, T1::SMEM_END)) return;
-                    k<<<grid, T1::THREADS, T1::SMEM_END, st>>>(g, m, s->scratch[0], s->scratch[1], s->scratch[2], sweep0, zchunk_, r, fa, s->d_dyn, s->d_flags, cf);
+                    k<<<grid, T1::THREADS, T1::SMEM_END, st>>>(g, m, s->scratch[0], s->scratch[1], s->scratch[2], sweep0, zchunk_, r, fa, s->d_dyn, s->d_flags, cf, s->d_passdbg);
                 } else {
                     auto k = maxw ? smk::k_pressure_tma<K, 16, false, true> : smk::k_pressure_tma<K, 16, false, false>;
                     if (ensure_smem(s, k, T0::SMEM_END)) return;
-                    k<<<grid, T0::THREADS, T0::SMEM_END, st>>>(g, m, s->scratch[0], s->scratch[1], s->scratch[2], sweep0, zchunk_, r, fa, s->d_dyn, s->d_flags, cf);
+                    k<<<grid, T0::THREADS, T0::SMEM_END, st>>>(g, m, s->scratch[0], s->scratch[1], s->scratch[2], sweep0, zchunk_, r, fa, s->d_dyn, s->d_flags, cf, s->d_passdbg);
                 }
+                s->passdbg_ctas = (int)(grid.x * grid.y * grid.z);
                 return;
             }
         }
@@ -1267,23 +1270,26 @@ EncodeTiledFn encode_tiled_fn()
     return (EncodeTiledFn)fn;
 }
 
-// tensor maps of the fused pressure pass over ONE arena (this slab's or a neighbour's): u, v, w [field][physical id] and
-// the two density buffers; box = 64 x 32 x 1 elements
-bool build_pass_maps(const GridP& g, char* arena, const ArenaLayout& lay, int nzn, int nzc, CUtensorMap (*node)[3], CUtensorMap* smoke, bool* smoke_ok)
+// tensor maps of the fused pressure pass over ONE arena (this slab's or a neighbour's): per physical buffer id one 4-D
+// tensor (x, y, z, field) over u, v, w -- the three arrays of a buffer set lie lay.v[id] - lay.u[id] bytes apart -- with
+// box 64 x 32 x 1 x 3, and the two density buffers (box 64 x 32 x 1)
+bool build_pass_maps(const GridP& g, char* arena, const ArenaLayout& lay, int nzn, int nzc, CUtensorMap* node, CUtensorMap* smoke, bool* smoke_ok)
 {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return false;
+    for (int id = 0; id < 3; id++) {
+        const size_t fs = lay.v[id] - lay.u[id];
+        if (lay.w[id] - lay.v[id] != fs || (fs & 15)) return false;
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        const cuuint32_t box[4] = {64, 32, 1, 3};
+        const cuuint64_t dims[4] = {(cuuint64_t)g.P, (cuuint64_t)g.SY, (cuuint64_t)nzn, 3};
+        const cuuint64_t str[3] = {(cuuint64_t)g.P * 4, (cuuint64_t)g.nplane * 4, (cuuint64_t)fs};
+        if (enc(&node[id], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, arena + lay.u[id], dims, str, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
     const cuuint32_t estr[3] = {1, 1, 1};
     const cuuint32_t box[3] = {64, 32, 1};
-    const cuuint64_t ndims[3] = {(cuuint64_t)g.P, (cuuint64_t)g.SY, (cuuint64_t)nzn};
-    const cuuint64_t nstr[2] = {(cuuint64_t)g.P * 4, (cuuint64_t)g.nplane * 4};
-    for (int f = 0; f < 3; f++)
-        for (int id = 0; id < 3; id++) {
-            const size_t off = f == 0 ? lay.u[id] : f == 1 ? lay.v[id] : lay.w[id];
-            if (enc(&node[f][id], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, arena + off, ndims, nstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-                return false;
-        }
     *smoke_ok = (g.W & 3) == 0 && nzc > 0;
     const cuuint64_t cdims[3] = {(cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)std::max(nzc, 1)};
     const cuuint64_t cstr[2] = {(cuuint64_t)g.W * 4, (cuuint64_t)g.cplane * 4};
@@ -1291,7 +1297,7 @@ bool build_pass_maps(const GridP& g, char* arena, const ArenaLayout& lay, int nz
         if (*smoke_ok && enc(&smoke[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, arena + lay.smoke[b], cdims, cstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             *smoke_ok = false;
-        if (!*smoke_ok) smoke[b] = node[0][0]; // never dereferenced (forcing then runs as its own kernel)
+        if (!*smoke_ok) smoke[b] = node[0]; // never dereferenced (forcing then runs as its own kernel)
     }
     return true;
 }
@@ -1409,6 +1415,10 @@ int create_common(smk_sim** out, unsigned W, unsigned H, unsigned D, int rank, i
         CKN(cudaMemsetAsync(s->cflag, 1, nb, s->stream)); // until the first k_codes run: assume COMPLEX cells everywhere
     }
     CKN(cudaMalloc(&s->d_scalar, 64));
+    if (getenv("SMK_PASS_DEBUG")) { CKN(cudaMalloc(&s->d_passdbg, (size_t)1 << 22)); CKN(cudaMemset(s->d_passdbg, 0, (size_t)1 << 22));
+        long long tile[3] = {1, 2, 1};
+        if (const char* e = getenv("SMK_TRACE_TILE")) sscanf(e, "%lld,%lld,%lld", &tile[0], &tile[1], &tile[2]);
+        CKN(cudaMemcpy(s->d_passdbg + (1 << 17) - 3, tile, sizeof(tile), cudaMemcpyHostToDevice)); }
     CKN(cudaMalloc(&s->d_dyn, 64));
     CKN(cudaMemsetAsync(s->d_dyn, 0, 64, s->stream));
     CKN(cudaMemsetAsync(s->code, 0, code_count(g), s->stream));
@@ -1538,7 +1548,7 @@ int smk_destroy(smk_sim* s)
         if (s->peer[i].arena && s->peer[i].ipc) cudaIpcCloseMemHandle(s->peer[i].arena);
     for (auto& d : s->schedules) { cudaFree(d.pieces); cudaFree(d.first); }
     cudaFree(s->arena);
-    cudaFree(s->mask); cudaFree(s->code); cudaFree(s->pcode); cudaFree(s->cflag); cudaFree(s->d_scalar); cudaFree(s->d_flags); cudaFree(s->d_dyn);
+    cudaFree(s->mask); cudaFree(s->code); cudaFree(s->pcode); cudaFree(s->cflag); cudaFree(s->d_scalar); cudaFree(s->d_flags); cudaFree(s->d_dyn); cudaFree(s->d_passdbg);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     cudaGetLastError();
     delete s;
@@ -1938,6 +1948,21 @@ int smk_reset_timers(smk_sim* s)
 }
 
 long smk_launch_count(smk_sim* s) { return s ? s->launches : -1; }
+
+// development aid: per-CTA {start clock, cycles, SM id, variant * 1000 + planes} of the last fused pass (SMK_PASS_DEBUG=1)
+int smk_debug_pass_ctas(smk_sim* s, long long* out4, int max_ctas)
+{
+    if (!s || !out4) return -SMK_ERR_ARG;
+    DeviceGuard dg(s);
+    if (!s->d_passdbg) return 0;
+    if (max_ctas < 0) { // trace region: 16 warps x 80 steps x 4 timestamps of one CTA
+        if (cudaStreamSynchronize(s->stream) != cudaSuccess || cudaMemcpy(out4, s->d_passdbg + (1 << 17), (size_t)17 * 80 * 8 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -SMK_ERR_CUDA;
+        return 17 * 80;
+    }
+    const int n = std::min(max_ctas, std::min(s->passdbg_ctas, 4096));
+    if (cudaStreamSynchronize(s->stream) != cudaSuccess || cudaMemcpy(out4, s->d_passdbg, (size_t)n * 32, cudaMemcpyDeviceToHost) != cudaSuccess) return -SMK_ERR_CUDA;
+    return n;
+}
 unsigned long long smk_readback_bytes(smk_sim* s) { return s ? s->readback_bytes : 0; }
 
 int smk_set_exchange(smk_sim* s, smk_exchange_fn fn, void* ctx)
