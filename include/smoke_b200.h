@@ -176,6 +176,15 @@ int smk_read_density_half(smk_sim* s, void* host_half);
  * channel) on the step's stream -- e.g. the array of the renderer's GL_R32F texture mapped through CUDA-GL interop.
  * Together with simulate(nullptr, dt) this removes the D2H + glTexSubImage3D round trip. */
 int smk_copy_density_to_array(smk_sim* s, void* cuda_array);
+/* SURVEY N1 as specified: bind the array once (NULL unbinds); from then on the density advection kernel writes every new
+ * density value into it with surf3Dwrite -- the whole W x H x D volume equals the "past" density buffer after each step,
+ * with no device-to-device pass and no host round trip (replaces cu:814 + boundingBox.cpp:380-385).  The array must allow
+ * surface load/store (cudaArraySurfaceLoadStore / a GL texture registered with cudaGraphicsRegisterFlagsSurfaceLoadStore). */
+int smk_bind_density_array(smk_sim* s, void* cuda_array);
+/* the solid mask as ONE BIT per cell (bit i of byte k = cell 8k + i in cell order, 1 = fluid;
+ * (W*H*D + 7) / 8 bytes).  smk_set_mask_bits has the semantics of smk_set_field(SMK_FIELD_MASK, ...) of the unpacked mask. */
+int smk_set_mask_bits(smk_sim* s, const unsigned char* bits);
+int smk_get_mask_bits(smk_sim* s, unsigned char* bits);
 /* test helpers: a plain 3-D float array standing in for the mapped texture */
 void* smk_test_array_create(unsigned W, unsigned H, unsigned D);
 int smk_test_array_read(void* cuda_array, float* host, unsigned W, unsigned H, unsigned D);

@@ -90,6 +90,9 @@ def load_library():
     L.smk_density_device.restype = _vp
     L.smk_set_stream.argtypes = [_vp, _vp]
     L.smk_copy_density_to_array.argtypes = [_vp, _vp]
+    L.smk_bind_density_array.argtypes = [_vp, _vp]
+    L.smk_set_mask_bits.argtypes = [_vp, _vp]
+    L.smk_get_mask_bits.argtypes = [_vp, _vp]
     L.smk_test_array_create.argtypes = [C.c_uint] * 3
     L.smk_test_array_create.restype = _vp
     L.smk_test_array_read.argtypes = [_vp, _vp] + [C.c_uint] * 3
@@ -229,6 +232,18 @@ class SmokeSim:
     def register_host(self, arr): self._ck(self.L.smk_register_host(self.h, arr.ctypes.data_as(_vp), arr.nbytes))
     def unregister_host(self, arr): self._ck(self.L.smk_unregister_host(self.h, arr.ctypes.data_as(_vp)))
     def copy_density_to_array(self, cuda_array): self._ck(self.L.smk_copy_density_to_array(self.h, cuda_array))
+    def bind_density_array(self, cuda_array): self._ck(self.L.smk_bind_density_array(self.h, cuda_array))
+
+    def set_mask_bits(self, bits):
+        """bits: uint8 array of (W*H*D + 7) // 8 bytes, np.packbits(mask.ravel(), bitorder='little')."""
+        b = np.ascontiguousarray(bits, dtype=np.uint8)
+        assert b.size == (self.W * self.H * self.D + 7) // 8
+        self._ck(self.L.smk_set_mask_bits(self.h, b.ctypes.data_as(_vp)))
+
+    def get_mask_bits(self):
+        b = np.zeros((self.W * self.H * self.D + 7) // 8, dtype=np.uint8)
+        self._ck(self.L.smk_get_mask_bits(self.h, b.ctypes.data_as(_vp)))
+        return b
 
     # -- stages
     def flip(self): self._ck(self.L.smk_stage_flip(self.h))

@@ -98,9 +98,10 @@ k_advect_velocity_tma(GridP g, const __grid_constant__ CUtensorMap mu, const __g
                       const __grid_constant__ CUtensorMap mw, const float* __restrict__ u0, const float* __restrict__ v0,
                       const float* __restrict__ w0, float* __restrict__ u1, float* __restrict__ v1, float* __restrict__ w1,
                       const unsigned char* __restrict__ code, float dt, int za, int zb, int zchunk, int2 zv,
-                      int* __restrict__ flag)
+                      int* __restrict__ flag, DynRange dr)
 {
     using A = AdvTma;
+    dyn_range(dr, za, zb);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* su = reinterpret_cast<float*>(smem_raw);
     float* sv = su + A::NSLOT * A::SLOT_FLOATS;

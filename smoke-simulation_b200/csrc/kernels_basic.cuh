@@ -438,6 +438,58 @@ __device__ __forceinline__ float avg_w8(const float* __restrict__ f, long long P
     return __fmul_rn(a, 0.125f);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Adaptive advection margin of a slab run: the reference passes wall-clock time as dt (main.cpp:891-895),
+// so a backtrace may reach any number of planes.  After the last pressure pass k_absmax_w reduces max |w| over the owned
+// planes (warp shuffles + one atomicMax per block) and k_margin turns it into M = planes of "now" data a node needs
+// beyond its own plane: ceil(dt * max|w|) for the backtrace + 1 for the trilinear corner (the 8-point averages need 1).
+// The advection launches read M from device memory: the planes at least M inside the slab are advected while the
+// ghost pull is in flight, the M-wide strips at the slab ends after it.  No host round trip, no fixed assumption on dt.
+__global__ void __launch_bounds__(256) k_absmax_w(const float4* __restrict__ w4, size_t n4, unsigned* __restrict__ out)
+{
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(w4 + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.f;
+        for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (threadIdx.x == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+    }
+}
+// dyn[0] = max |w| bits (reset here), dyn[1] = margin M in planes (clamped to the ghost depth: beyond that the device-side
+// guard of the samplers raises SMK_ERR_REACH -- the ghost allocation itself is then too small), dyn[2] = unclamped M
+__global__ void k_margin(unsigned* __restrict__ dyn, float dt, int ghost)
+{
+    const float r = __uint_as_float(dyn[0]) * fabsf(dt) * 1.000001f; // (the 8-point average may exceed max |w| by a few ulp)
+    int M = (r < 1.0e6f ? (int)ceilf(r) : 1000000) + 1;
+    if (M < 2) M = 2;
+    dyn[2] = (unsigned)M;
+    dyn[1] = (unsigned)min(M, ghost);
+    dyn[0] = 0u;
+}
+// plane range of an advection launch as a function of the margin: mode 0 = [za, zb) as given; 1 = the planes at least M
+// inside the slab; 2 / 3 = the strip below / above them.  own_lo / own_hi = first / last owned node plane, or far
+// outside the grid on a side without a neighbour.
+struct DynRange {
+    const unsigned* dyn;
+    int mode, own_lo, own_hi;
+};
+__device__ __forceinline__ void dyn_range(const DynRange& d, int& za, int& zb)
+{
+    if (d.mode == 0) return;
+    const int M = (int)d.dyn[1];
+    const int lo = d.own_lo + M, hi = max(lo, d.own_hi - M + 1); // interior [lo, hi); empty when the slab is thinner than 2M
+    if (d.mode == 1) { za = max(za, lo); zb = min(zb, hi); }
+    else if (d.mode == 2) zb = min(zb, lo);
+    else za = max(za, hi);
+}
+
 // (float)((double)i + 0.5): the reference evaluates "y + 0.5" in double and narrows (cu:536-537)
 __device__ __forceinline__ float half_up(int i) { return __double2float_rn(__dadd_rn((double)i, 0.5)); }
 
@@ -453,8 +505,9 @@ __global__ void __launch_bounds__(256) k_advect_velocity(GridP g, const float* _
                                                          const float* __restrict__ v0, const float* __restrict__ w0,
                                                          float* __restrict__ u1, float* __restrict__ v1,
                                                          float* __restrict__ w1, const unsigned char* __restrict__ code,
-                                                         float dt, int za, int zb, int2 zv, int* __restrict__ flag)
+                                                         float dt, int za, int zb, int2 zv, int* __restrict__ flag, DynRange dr)
 {
+    dyn_range(dr, za, zb);
     // 3-D thread blocks (32 x BY x BZ nodes): the 3x3x3 neighbourhoods of a block overlap in L1
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -541,6 +594,59 @@ __global__ void __launch_bounds__(256) k_advect_smoke32(GridP g, const float* __
     const float pz = __double2float_rn(__dadd_rn(__dadd_rn((double)z, 0.5), (double)mw));
     const float bx = (float)(unsigned)(g.W - 1), by = (float)(unsigned)(g.H - 1), bz = (float)(unsigned)(g.D - 1);
     s1[x + y * g.W + zr * cpl] = sample_global32(s0, g.W, cpl, g.zlo, px, py, pz, .5f, .5f, .5f, bx, by, bz, zv, flag);
+}
+
+// the same kernel writing the new density ALSO into a 3-D surface (the renderer's GL_R32F texture mapped
+// through CUDA-GL interop, boundingBox.cpp:364-385) instead of going device -> host -> glTexSubImage3D (cu:814).  The
+// surface must equal the "past" buffer everywhere, including the cells advection never writes (boundary shell, solids:
+// they keep the buffer's stale value), so this variant visits every cell of the planes [za, zb).
+__global__ void __launch_bounds__(256) k_advect_smoke_surf(GridP g, const float* __restrict__ s0, float* __restrict__ s1,
+                                                           const float* __restrict__ u, const float* __restrict__ v,
+                                                           const float* __restrict__ w, const unsigned char* __restrict__ code,
+                                                           float dt, int za, int zb, int2 zv, int* __restrict__ flag,
+                                                           cudaSurfaceObject_t surf)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int z = za + blockIdx.z * blockDim.z + threadIdx.z;
+    if (x >= g.W || y >= g.H || z >= zb) return;
+    const long long c = cell_index(g, x, y, z);
+    float val;
+    const bool interior = x >= 1 && y >= 1 && z >= 1 && x < g.W - 1 && y < g.H - 1 && z < g.D - 1;
+    if (interior && (code[code_index(g, x, y, z)] & CODE_SELF)) {
+        const long long n = node_index(g, x, y, z);
+        const float mu = __fmul_rn(__fmul_rn(__fadd_rn(u[n], u[n + 1]), -0.5f), dt);
+        const float mv = __fmul_rn(__fmul_rn(__fadd_rn(v[n], v[n + g.P]), -0.5f), dt);
+        const float mw = __fmul_rn(__fmul_rn(__fadd_rn(w[n], w[n + g.nplane]), -0.5f), dt);
+        const float px = __double2float_rn(__dadd_rn(__dadd_rn((double)x, 0.5), (double)mu));
+        const float py = __double2float_rn(__dadd_rn(__dadd_rn((double)y, 0.5), (double)mv));
+        const float pz = __double2float_rn(__dadd_rn(__dadd_rn((double)z, 0.5), (double)mw));
+        const float bx = (float)(unsigned)(g.W - 1), by = (float)(unsigned)(g.H - 1), bz = (float)(unsigned)(g.D - 1);
+        val = sample_global(s0, g.W, g.cplane, g.zlo, px, py, pz, .5f, .5f, .5f, bx, by, bz, zv, flag);
+        s1[c] = val;
+    } else {
+        val = s1[c];
+    }
+    surf3Dwrite(val, surf, x * (int)sizeof(float), y, z);
+}
+
+// the solid mask as ONE BIT per cell at the boundary (bit i of byte k = cell 8k + i in the
+// reference's cell order; 1 = fluid) -- an eighth of the bytes for voxelised obstacles (N3) uploaded or read back.
+__global__ void __launch_bounds__(256) k_mask_unpack(const unsigned char* __restrict__ bits, unsigned char* __restrict__ mask, size_t first_cell, size_t ncells)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncells) return;
+    const size_t c = first_cell + i;
+    mask[i] = (bits[c >> 3] >> (c & 7)) & 1u;
+}
+__global__ void __launch_bounds__(256) k_mask_pack(const unsigned char* __restrict__ mask, unsigned char* __restrict__ bits, size_t first_cell, size_t ncells)
+{
+    // one thread per output byte of the packed range (first_cell is a multiple of 8: the host checks)
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k * 8 >= ncells) return;
+    unsigned b = 0;
+    for (int j = 0; j < 8 && k * 8 + j < ncells; j++) b |= (mask[k * 8 + j] != 0 ? 1u : 0u) << j;
+    bits[(first_cell >> 3) + k] = (unsigned char)b;
 }
 
 // ---------------------------------------------------------------------------------------------------

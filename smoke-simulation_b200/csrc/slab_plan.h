@@ -18,9 +18,12 @@
 
 namespace slab {
 
-constexpr int MARGIN = 2; // planes of "now" data needed beyond an advected plane: 1 (8-point averages) and
-                          // floor/ceil of a backtrace shorter than one cell + the trilinear corner;
-                          // longer backtraces are caught by the device-side guard (SMK_ERR_REACH)
+constexpr int MARGIN = 2; // the LEAST planes of "now" data needed beyond an advected plane: 1 (8-point averages), and
+                          // floor/ceil of a backtrace shorter than one cell + the trilinear corner.
+                          // dt is wall-clock time in the reference (main.cpp:891-895): longer backtraces are served by
+                          // refreshing the WHOLE ghost depth in front of advection (below) and by the adaptive margin of
+                          // the overlapped peer-memory path (smk_api.cu compute_margin); SMK_ERR_REACH is left for reaches
+                          // beyond the ghost allocation itself (device-side guard of the samplers)
 
 enum OpKind { OP_FLIP = 0, OP_FILL = 1, OP_FORCE = 2, OP_PRESSURE = 3, OP_ADVECT_VEL = 4, OP_ADVECT_SMOKE = 5, OP_EXCHANGE = 6 };
 enum SetId { SET_VEL_NOW = 0, SET_SMOKE_NOW = 1 };
@@ -138,14 +141,14 @@ inline std::vector<Op> plan_step(const Geom& g, int iterations, int fuse, Carry&
     // advection of the top owned cell plane reads the NEW w on its upper face (node fields store one more plane above)
     const int va = std::max(1, g.c0), vb = std::min(D - 1, g.has_upper() ? g.c1 : D - 1); // inclusive
     {
-        if (vel_d < MARGIN) exchange(SET_VEL_NOW);
+        if (vel_d < G) exchange(SET_VEL_NOW); // the full ghost depth: a backtrace may reach ghost - 1 planes
         const Interval v = node_interval(g, vel_d);
         ops.push_back({OP_ADVECT_VEL, va, vb + 1, v.lo, g.has_upper() ? v.hi + 1 : v.hi});
     }
     // density advection: interior cell planes of the slab
     const int sa = std::max(1, g.c0), sb = std::min(D - 2, g.c1 - 1); // inclusive
     {
-        if (smoke_d < MARGIN) exchange(SET_SMOKE_NOW);
+        if (smoke_d < G) exchange(SET_SMOKE_NOW);
         const Interval v = cell_interval(g, smoke_d);
         ops.push_back({OP_ADVECT_SMOKE, sa, sb + 1, v.lo, v.hi});
     }

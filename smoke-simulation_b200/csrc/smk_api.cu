@@ -149,6 +149,8 @@ struct smk_sim {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_snap = nullptr, ev_copied = nullptr;
     cudaEvent_t ev_chunk[8] = {}; // chunked blocking readback (enqueue_step)
+    cudaSurfaceObject_t density_surf = 0; // smk_bind_density_array: the density advection also writes this 3-D surface (N1)
+    cudaArray_t density_array = nullptr;
     float* snapshot = nullptr;
     void* half_stage = nullptr; // binary16 staging buffer of smk_read_density_half
     bool copy_pending = false;
@@ -866,11 +868,14 @@ int stage_pressure(smk_sim* s)
 }
 
 // node planes [za, zb); [vlo, vhi] = planes of the "now" velocities that hold valid data (reach guard)
-int stage_advect_velocity(smk_sim* s, float dt, int za, int zb, int vlo, int vhi)
+int stage_advect_velocity(smk_sim* s, float dt, int za, int zb, int vlo, int vhi, int dyn_mode = 0)
 {
     const GridP& g = s->g;
     Span sp(s, SMK_STAGE_ADVECT_VEL);
     const int n = s->now, p = s->past;
+    // dynamic plane range (adaptive margin, kernels_basic.cuh): sides without a neighbour never shrink
+    const smk::DynRange dr{s->d_dyn, dyn_mode, s->geom.has_lower() ? s->geom.own_node_lo() : -(1 << 28),
+                           s->geom.has_upper() ? s->geom.own_node_hi() : (1 << 28)};
     za = std::max(za, std::max(1, g.zlo));
     zb = std::min(zb, std::min(g.D, g.zlo + g.nzc));
     if (zb > za) {
@@ -886,12 +891,12 @@ int stage_advect_velocity(smk_sim* s, float dt, int za, int zb, int vlo, int vhi
             const dim3 grd((g.W + A::TX - 1) / A::TX, (g.H + A::TY - 1) / A::TY, (zb - za + zchunk - 1) / zchunk);
             smk::k_advect_velocity_tma<<<grd, A::THREADS, A::SMEM, s->stream>>>(
                 g, s->tmap[0][id], s->tmap[1][id], s->tmap[2][id], s->u[n], s->v[n], s->w[n], s->u[p], s->v[p], s->w[p], s->code, dt,
-                za, zb, zchunk, make_int2(vlo, vhi), s->d_flags);
+                za, zb, zchunk, make_int2(vlo, vhi), s->d_flags, dr);
         } else {
             const int by = 4, bz = 2; // block shape is immaterial (issue-bound; measured 32x4x2 .. 32x8x1 within 1 %)
             const dim3 blk(32, by, bz), grd((g.W + 31) / 32, (g.H + by - 1) / by, (zb - za + bz - 1) / bz);
             smk::k_advect_velocity<<<grd, blk, 0, s->stream>>>(
-                g, s->u[n], s->v[n], s->w[n], s->u[p], s->v[p], s->w[p], s->code, dt, za, zb, make_int2(vlo, vhi), s->d_flags);
+                g, s->u[n], s->v[n], s->w[n], s->u[p], s->v[p], s->w[p], s->code, dt, za, zb, make_int2(vlo, vhi), s->d_flags, dr);
         }
         count_launch(s, SMK_STAGE_ADVECT_VEL);
     }
@@ -905,6 +910,8 @@ int stage_advect_smoke(smk_sim* s, float dt, int za, int zb, int vlo, int vhi)
     const GridP& g = s->g;
     Span sp(s, SMK_STAGE_ADVECT_SMOKE);
     const int n = s->now, p = s->past;
+    // (surface variant: the requested planes widened to the boundary planes 0 and D-1 when the request touches plane 1 / D-2)
+    const int za0 = za <= 1 ? 0 : za, zb0 = zb >= g.D - 1 ? g.D : zb;
     za = std::max(za, std::max(1, g.zlo));
     zb = std::min(zb, std::min(g.D - 1, g.zlo + g.nzc));
     if (zb > za) {
@@ -914,9 +921,20 @@ int stage_advect_smoke(smk_sim* s, float dt, int za, int zb, int vlo, int vhi)
         static const bool idx64 = getenv("SMK_ADVECT_IDX64") != nullptr;
         const bool small = !idx64 && (size_t)g.nplane * g.nzn < ((size_t)1 << 31) && (size_t)g.kplane * g.nzc < ((size_t)1 << 31);
         auto kern = small ? smk::k_advect_smoke32 : smk::k_advect_smoke;
-        kern<<<grd, blk, 0, s->stream>>>(
-            g, s->smoke[n], s->smoke[p], s->u[p], s->v[p], s->w[p], s->code, dt, za, zb, make_int2(vlo, vhi), s->d_flags);
+        if (!s->density_surf)
+            kern<<<grd, blk, 0, s->stream>>>(
+                g, s->smoke[n], s->smoke[p], s->u[p], s->v[p], s->w[p], s->code, dt, za, zb, make_int2(vlo, vhi), s->d_flags);
         count_launch(s, SMK_STAGE_ADVECT_SMOKE);
+    }
+    if (s->density_surf) { // N1: every owned cell plane goes to the bound surface too (incl. the planes advection never writes)
+        const int sa = std::max(za0, s->geom.c0), sb = std::min(zb0, s->geom.c1);
+        if (sb > sa) {
+            const int by = 4, bz = 2;
+            const dim3 blk(32, by, bz), grd((g.W + 31) / 32, (g.H + by - 1) / by, (sb - sa + bz - 1) / bz);
+            smk::k_advect_smoke_surf<<<grd, blk, 0, s->stream>>>(g, s->smoke[n], s->smoke[p], s->u[p], s->v[p], s->w[p], s->code, dt, sa, sb,
+                                                               make_int2(vlo, vhi), s->d_flags, s->density_surf);
+            if (zb <= za) count_launch(s, SMK_STAGE_ADVECT_SMOKE);
+        }
     }
     CK(s, cudaGetLastError());
     return SMK_OK;
@@ -1077,7 +1095,22 @@ int exec_op(smk_sim* s, const slab::Op& op, float dt)
 bool overlap_exchange_ok(const smk_sim* s, const slab::Op& adv)
 {
     static const bool off = getenv("SMK_P2P_NO_OVERLAP") != nullptr;
-    return s->p2p && !off && s->geom.world > 1 && adv.b - adv.a >= 8 + 2 * slab::MARGIN;
+    // (rank-invariant: every rank must take the same decision, the handshakes of the two variants differ)
+    return s->p2p && !off && s->geom.world > 1 && s->geom.D / s->geom.world - 1 >= 8 + 2 * slab::MARGIN && adv.b - adv.a >= 8 + 2 * slab::MARGIN;
+}
+
+// max |w| over the owned planes of the "now" velocities -> advection margin in d_dyn[1] (kernels_basic.cuh)
+int compute_margin(smk_sim* s, float dt)
+{
+    const GridP& g = s->g;
+    const int lo = s->geom.own_node_lo(), hi = s->geom.own_node_hi();
+    const size_t n4 = (size_t)(hi - lo + 1) * g.nplane / 4;
+    const float4* w4 = reinterpret_cast<const float4*>(s->w[s->now] + (size_t)(lo - g.zlo) * g.nplane);
+    smk::k_absmax_w<<<(unsigned)std::min<size_t>((n4 + 255) / 256, (size_t)8 * s->num_sms), 256, 0, s->stream>>>(w4, n4, s->d_dyn);
+    smk::k_margin<<<1, 1, 0, s->stream>>>(s->d_dyn, dt, s->geom.ghost);
+    s->launches += 2;
+    CK(s, cudaGetLastError());
+    return SMK_OK;
 }
 
 int exchange_overlapped_with_advect(smk_sim* s, const slab::Op& adv, float dt, bool with_smoke)
@@ -1101,14 +1134,18 @@ int exchange_overlapped_with_advect(smk_sim* s, const slab::Op& adv, float dt, b
     if ((rc = p2p_pull(s, slab::SET_VEL_NOW, s->aux_stream))) return rc;
     if (with_smoke && (rc = p2p_pull(s, slab::SET_SMOKE_NOW, s->aux_stream))) return rc;
     CK(s, cudaEventRecord(s->ev_join, s->aux_stream));
-    // interior: every plane within MARGIN of an output plane is an owned plane (never written by the pull)
+    // While the pull is in flight: the planes at least M inside the slab, M = the margin the projected velocities ask for
+    // (compute_margin: on the device, read by the launches below -- a frame hitch with a large dt widens the strips
+    // instead of failing).  Every plane such a node reads is an owned plane, never written by the pull.
+    if ((rc = compute_margin(s, dt))) return rc;
     const slab::Geom& ge = s->geom;
-    const int lo = ge.has_lower() ? std::max(adv.a, ge.own_node_lo() + slab::MARGIN) : adv.a;
-    const int hi = ge.has_upper() ? std::min(adv.b, ge.own_node_hi() - slab::MARGIN + 1) : adv.b;
-    if ((rc = stage_advect_velocity(s, dt, lo, hi, std::max(adv.p0, ge.own_node_lo()), std::min(adv.p1, ge.own_node_hi())))) return rc;
+    const int G = ge.ghost;
+    if ((rc = stage_advect_velocity(s, dt, adv.a, adv.b, ge.own_node_lo(), ge.own_node_hi(), 1))) return rc;
     CK(s, cudaStreamWaitEvent(s->stream, s->ev_join, 0));
-    if (lo > adv.a && (rc = stage_advect_velocity(s, dt, adv.a, lo, adv.p0, adv.p1))) return rc;
-    if (adv.b > hi && (rc = stage_advect_velocity(s, dt, hi, adv.b, adv.p0, adv.p1))) return rc;
+    // ... then the strips at the slab ends (at most `ghost` planes each; the launches size themselves from M), with every
+    // stored plane valid
+    if (ge.has_lower() && (rc = stage_advect_velocity(s, dt, adv.a, std::min(adv.b, ge.own_node_lo() + G), adv.p0, adv.p1, 2))) return rc;
+    if (ge.has_upper() && (rc = stage_advect_velocity(s, dt, std::max(adv.a, ge.own_node_hi() - G + 1), adv.b, adv.p0, adv.p1, 3))) return rc;
     return SMK_OK;
 }
 
@@ -1539,6 +1576,7 @@ int smk_destroy(smk_sim* s)
     if (s->ev_snap) cudaEventDestroy(s->ev_snap);
     for (auto& e : s->ev_chunk) if (e) cudaEventDestroy(e);
     if (s->ev_copied) cudaEventDestroy(s->ev_copied);
+    if (s->density_surf) cudaDestroySurfaceObject(s->density_surf);
     cudaFree(s->snapshot);
     cudaFree(s->half_stage);
     while (!s->registered.empty()) drop_registration(s, s->registered.size() - 1);
@@ -1743,12 +1781,77 @@ int smk_copy_density_to_array(smk_sim* s, void* cuda_array)
     return SMK_OK;
 }
 
+// SURVEY N1 as specified: bind the array ONCE; from then on the density advection itself writes every new density value
+// into it with surf3Dwrite (k_advect_smoke_surf) -- no device-to-device pass, no host round trip.  NULL unbinds.
+int smk_bind_density_array(smk_sim* s, void* cuda_array)
+{
+    if (!s) return SMK_ERR_ARG;
+    DeviceGuard dg(s);
+    CK(s, cudaStreamSynchronize(s->stream));
+    if (s->density_surf) { cudaDestroySurfaceObject(s->density_surf); s->density_surf = 0; s->density_array = nullptr; }
+    if (!cuda_array) return SMK_OK;
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = static_cast<cudaArray_t>(cuda_array);
+    CK(s, cudaCreateSurfaceObject(&s->density_surf, &rd));
+    s->density_array = static_cast<cudaArray_t>(cuda_array);
+    return SMK_OK;
+}
+
+// the mask as one bit per cell (bit i of byte k = cell 8k + i, 1 = fluid), W*H*D/8 bytes (rounded up).
+// smk_set_mask_bits == smk_set_field(SMK_FIELD_MASK) of the unpacked bytes (the stencil codes are rebuilt, the obstacle
+// list is re-applied by the next fill like the reference would, cu:289-313); a slab touches the planes it stores.
+int smk_set_mask_bits(smk_sim* s, const unsigned char* bits)
+{
+    if (!s || !bits) return SMK_ERR_ARG;
+    DeviceGuard dg(s);
+    const GridP& g = s->g;
+    const size_t total = (size_t)g.cplane * g.D, first = (size_t)g.mzlo * g.cplane, n = (size_t)g.nzm * g.cplane;
+    unsigned char* d = nullptr;
+    CK(s, cudaMalloc(&d, (total + 7) / 8));
+    cudaError_t e = cudaMemcpyAsync(d, bits, (total + 7) / 8, cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) {
+        smk::k_mask_unpack<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(d, s->mask, first, n);
+        s->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(s, SMK_ERR_CUDA, std::string("smk_set_mask_bits: ") + cudaGetErrorString(e));
+    s->carry = slab::initial_carry(s->geom);
+    s->mask_dirty = true;
+    launch_codes(s);
+    CK(s, cudaGetLastError());
+    CK(s, cudaStreamSynchronize(s->stream));
+    return SMK_OK;
+}
+
+int smk_get_mask_bits(smk_sim* s, unsigned char* bits)
+{
+    if (!s || !bits) return SMK_ERR_ARG;
+    DeviceGuard dg(s);
+    const GridP& g = s->g;
+    const size_t first = (size_t)g.mzlo * g.cplane, n = (size_t)g.nzm * g.cplane;
+    if (first % 8) return fail(s, SMK_ERR_ARG, "smk_get_mask_bits: the slab's first stored cell is not on a byte boundary of the packed mask");
+    unsigned char* d = nullptr;
+    const size_t nb = (n + 7) / 8;
+    CK(s, cudaMalloc(&d, nb));
+    smk::k_mask_pack<<<(unsigned)((nb + 255) / 256), 256, 0, s->stream>>>(s->mask, d - (first >> 3), first, n);
+    s->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bits + (first >> 3), d, nb, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(s, SMK_ERR_CUDA, std::string("smk_get_mask_bits: ") + cudaGetErrorString(e));
+    return SMK_OK;
+}
+
 // test helpers for the above (a plain 3-D float array stands in for the mapped GL texture)
 void* smk_test_array_create(unsigned W, unsigned H, unsigned D)
 {
     cudaArray_t a = nullptr;
     cudaChannelFormatDesc d = cudaCreateChannelDesc<float>();
-    if (cudaMalloc3DArray(&a, &d, make_cudaExtent(W, H, D)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaMalloc3DArray(&a, &d, make_cudaExtent(W, H, D), cudaArraySurfaceLoadStore) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return a;
 }
 int smk_test_array_read(void* cuda_array, float* host, unsigned W, unsigned H, unsigned D)

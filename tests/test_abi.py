@@ -83,3 +83,21 @@ def test_fails_loudly_without_gpu(smk):
         pytest.skip("a GPU is present")
     with pytest.raises(smk.SmokeError):
         smk.SmokeSim(8, 8, 8)
+
+
+def test_smoke_run_builds_against_the_c_abi_and_rejects_bad_scenes(tmp_path):
+    """host/smoke_run.cpp is plain C++ over include/smoke_b200.h (no CUDA header); without a GPU it must fail
+    loudly in smk_create, and a malformed scene file is reported with its line."""
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(ROOT, "smoke-simulation_b200", "host")
+    exe = str(tmp_path / "smoke_run")
+    subprocess.run(["/usr/bin/g++", "-O2", "-Wall", "-Werror", os.path.join(host, "smoke_run.cpp"), "-I" + os.path.join(ROOT, "include"),
+                    "-L" + os.path.dirname(host), "-lsmoke_b200", "-Wl,-rpath," + os.path.dirname(host), "-o", exe], check=True)
+    bad = tmp_path / "bad.scene"
+    bad.write_text("grid 8 8 8\nsauce 1 2 3 4\n")
+    r = subprocess.run([exe, "--scene", str(bad)], capture_output=True, text=True)
+    assert r.returncode == 2 and "bad.scene:2" in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "--scene", "C1", "--ticks", "1"], capture_output=True, text=True)
+        assert r.returncode == 2 and "smk_create" in r.stderr

@@ -147,3 +147,49 @@ def test_c2_256_60_ticks_identical_to_reference_gpu_build(po, smk):
         assert float(np.abs(v).max()) > 5.0          # a developed plume, not the first puff
     finally:
         r.close(); a.close()
+
+
+def test_density_surface_write_equals_the_density_buffer(po, smk):
+    """SURVEY N1 as specified: with a 3-D array bound (smk_bind_density_array) the density advection kernel itself writes the
+    new density with surf3Dwrite; after every step the array must equal the "past" density buffer in EVERY cell -- the
+    boundary shell and solid cells advection never writes included -- and the oracle's density.  simulate(nullptr, dt)."""
+    import ctypes
+    n = 40
+    sc = po.scaled_scene("C1", n)
+    a, b = make_pair(po, smk, sc)
+    L = smk.load_library()
+    arr = L.smk_test_array_create(n, n, n)
+    assert arr
+    a.bind_density_array(arr)
+    out = np.full((n, n, n), -3.0, dtype=np.float32)
+    for t in range(5):
+        a.step(po.tick_dt(t), None); b.step(po.tick_dt(t))
+        a.sync()
+        assert L.smk_test_array_read(arr, out.ctypes.data_as(ctypes.c_void_p), n, n, n) == 0
+        assert np.array_equal(out, a.get_field(po.SMOKE, po.PAST)), f"array != device density at tick {t}"
+        assert np.array_equal(out, b.get_field(po.SMOKE, po.PAST)), f"array != oracle density at tick {t}"
+    compare(po, a, b, "surface-write variant")
+    a.bind_density_array(None)
+    a.step(0.05, None); b.step(0.05)
+    compare(po, a, b, "after unbinding")
+    L.smk_test_array_destroy(arr)
+    a.close()
+
+
+def test_bit_packed_mask_round_trip_and_step(po, smk):
+    """a voxelised solid uploaded as one bit per cell == the same mask uploaded as bytes (steps identical
+    to the oracle); reading the packed mask back returns the bits."""
+    W, H, D = 24, 20, 18
+    vox = np.ones((D, H, W), dtype=np.uint8); vox[:, 0, :] = 0; vox[6:12, 8:11, 5:19] = 0; vox[3, 5, 7] = 0
+    bits = np.packbits(vox.ravel(), bitorder="little")
+    a = smk.SmokeSim(W, H, D); b = po.Oracle(W, H, D)
+    for e in (a, b):
+        e.add_source(12, 4, 9, 3.0)
+    a.set_mask_bits(bits); b.set_field(po.MASK, po.NOW, vox)
+    assert np.array_equal(a.get_field(po.MASK), vox)
+    assert np.array_equal(a.get_mask_bits(), bits)
+    for t in range(4):
+        a.step(po.tick_dt(t)); b.step(po.tick_dt(t))
+    compare(po, a, b, "bit-packed voxel mask")
+    assert np.array_equal(np.unpackbits(a.get_mask_bits(), bitorder="little")[:W * H * D].reshape(D, H, W), vox)
+    a.close()

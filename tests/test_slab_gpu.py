@@ -70,6 +70,24 @@ def test_virtual_slabs_bit_identical_to_single_gpu(po, smk, world, ghost, fuse, 
                                                    (2, 6, 2, (20, 18, 30)), (2, 8, 4, (256, 256, 160))])
 @pytest.mark.parametrize("ctas", [0, 3, 148])
 def test_peer_memory_path_bit_identical_to_single_gpu(po, smk, world, ghost, fuse, dims, ctas):
+    _peer_memory_run(po, smk, world, ghost, fuse, dims, ctas, [0.05, 0.05, 0.05])
+
+
+@pytest.mark.parametrize("world,ghost,dims,dts,expect_reach", [(2, 8, (70, 40, 48), [0.05, 0.5, 0.05], False), (3, 6, (40, 30, 60), [0.5, 0.05], False),
+                                                              (2, 8, (70, 40, 48), [0.05, 16.0], True)])
+def test_slabs_survive_a_frame_hitch(po, smk, world, ghost, dims, dts, expect_reach):
+    """dt is wall-clock time in the reference (main.cpp:891-895).  A tick with dt = 0.5 on random u, v, w ~ U(-4, 4) backtraces 2-3
+    planes across the slab boundary: the ghost refresh in front of advection covers the whole ghost depth, so the slabs stay
+    bit-identical to the single-GPU run.  Only a reach beyond the ghost allocation itself (dt = 16: the clamp bounds the reach by 3 sqrt(dt) = 12 planes, ghost 8) is an
+    error, and it is reported (SMK_ERR_REACH), never a silent stale read."""
+    if expect_reach:
+        with pytest.raises(smk.SmokeError, match="error 4"):
+            _peer_memory_run(po, smk, world, ghost, 4, dims, 0, dts)
+    else:
+        _peer_memory_run(po, smk, world, ghost, 4, dims, 0, dts)
+
+
+def _peer_memory_run(po, smk, world, ghost, fuse, dims, ctas, dts):
     """The B200-native transport: pressure passes read the neighbours' boundary planes straight from their memory
     (epoch handshake per pass, no ghost copies), halo refreshes before advection are pulls over the mapped memory.
     Virtual slabs in one process (pointer attach instead of CUDA IPC); every rank just runs smk_step_async.
@@ -80,7 +98,7 @@ def test_peer_memory_path_bit_identical_to_single_gpu(po, smk, world, ghost, fus
     same epoch values per pass."""
     from smoke_simulation_b200 import slab
     W, H, D = dims
-    iterations, steps, dt = 7, 3, 0.05
+    iterations, steps = 7, len(dts)
     scene = (W, H, D, -9.82, 3.0, [(W / 2, H / 2, D / 2, 2.5)], [(W / 2, H / 3, D / 3, 2.0)])
     st = random_state(po, W, H, D, seed=5)
     ref = smk.SmokeSim(W, H, D); po.setup_scene(ref, scene); inject(po, ref, st); ref.set_solver(0, iterations, fuse)
@@ -94,15 +112,18 @@ def test_peer_memory_path_bit_identical_to_single_gpu(po, smk, world, ghost, fus
     # slab's wait (streams may share a hardware queue; in the real multi-process run each GPU simply calls smk_step).
     plans = [slab.plan_p2p(W, H, D, world, r, ghost, iterations, fuse, steps) for r in range(world)]
     assert len({len(p) for p in plans}) == 1
+    step_i = -1
     for i in range(len(plans[0])):
         op = plans[0][i]
+        if op[0] == "flip":
+            step_i += 1
         if op[0] == "exchange" or (op[0] == "pressure" and op[4] == 4):
             for s in sims:
                 s.p2p_presignal()
         for s, p in zip(sims, plans):
-            s.exec_op(p[i], dt)
+            s.exec_op(p[i], dts[step_i])
     for t in range(steps):
-        ref.step(dt)
+        ref.step(dts[t])
     for s in sims:
         s.sync()
     assert all(s.exchange_count() >= steps for s in sims)

@@ -23,6 +23,7 @@ from conftest import inject, random_state  # noqa: E402
 def main():
     transport = sys.argv[1] if len(sys.argv) > 1 else "p2p"
     W, H, dper = (int(v) for v in sys.argv[2:5]) if len(sys.argv) >= 5 else (64, 48, 40)
+    mode = sys.argv[5] if len(sys.argv) > 5 else "plain"   # plain | hitch (one tick with dt = 0.5) | reach (dt too large for the ghost planes)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -40,9 +41,27 @@ def main():
         keep = smk.slab.TorchTransport(rank, world); sim.set_exchange(keep)
     dist.barrier()
     host = np.zeros((D, H, W), dtype=np.float32); ref_host = np.zeros_like(host)
+    dts = [po.tick_dt(t) for t in range(steps)]
+    if mode == "hitch":
+        dts[2] = 0.5          # u, v, w ~ U(-4, 4) after projection: backtraces of 2-3 planes (the reference passes wall-clock dt)
+    if mode == "reach":
+        dts[1] = 16.0         # the clamp bounds the reach by 3 sqrt(dt) = 12 planes: beyond ghost - 1 -> every slab rank must raise SMK_ERR_REACH, not return stale data
+    reach_err = 0
     for t in range(steps):
-        sim.step(po.tick_dt(t), host)
-        ref.step(po.tick_dt(t), ref_host)
+        try:
+            sim.step(dts[t], host)
+        except smk.SmokeError as ex:
+            if mode == "reach" and "error 4" in str(ex):
+                reach_err = 1
+                break
+            raise
+        ref.step(dts[t], ref_host)
+    if mode == "reach":
+        tot = torch.tensor([reach_err], device="cuda"); dist.all_reduce(tot, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"mp_check {transport} world={world} grid={W}x{H}x{D} reach: " + ("OK (SMK_ERR_REACH raised on every rank)" if int(tot.item()) else "FAILED (no SMK_ERR_REACH)"), flush=True)
+        sim.close(); ref.close(); dist.barrier(); dist.destroy_process_group()
+        sys.exit(0 if int(tot.item()) else 1)
     g = smk.slab.geometry(W, H, D, world, rank, ghost)
     bad = []
     for f, name in ((po.U, "u"), (po.V, "v"), (po.W, "w")):
@@ -60,7 +79,7 @@ def main():
     if bad:
         print(f"rank {rank}: MISMATCH {bad}", flush=True)
     if rank == 0:
-        print(f"mp_check {transport} world={world} grid={W}x{H}x{D} exchanges/step={sim.exchange_count() / steps:.1f}:",
+        print(f"mp_check {transport} world={world} grid={W}x{H}x{D} mode={mode} exchanges/step={sim.exchange_count() / steps:.1f}:",
               "OK (bit-identical to the single-GPU run)" if int(ok.item()) else "FAILED", flush=True)
     sim.close(); ref.close()
     dist.barrier()
