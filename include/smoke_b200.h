@@ -136,6 +136,13 @@ int smk_set_pass_ctas(smk_sim* s, int nctas);
 /* CTAs of the most recent pressure pass if it ran on balanced piece lists, 0 if it ran as a (tile, z-chunk) grid */
 int smk_last_pass_ctas(smk_sim* s);
 
+/* sparse blocking readback (extension, single GPU, off by default; SMK_READBACK_BOX=1 turns it on for every simulation):
+ * smk_step(sim, dt, host) copies only the rows that can hold non-zero density -- the rows the previous readback into
+ * the SAME buffer found non-zero, grown by two cells -- and falls back to the full copy when the new density is not
+ * covered (checked on the device every step).  The buffer ends up identical to the reference's full copy (cu:814) as long
+ * as the caller does not write to it between steps.  smk_readback_bytes() counts what was actually moved. */
+int smk_set_readback_box(smk_sim* s, int on);
+
 /* ---- the step ---------------------------------------------------------------------------------------- */
 
 /* replaces simulate(float* smoke_grid, float dt)  (smokeSimulation.cuh:5, cu:774-819).

@@ -76,6 +76,7 @@ def load_library():
     L.smk_buoyancy_ptr.restype = C.POINTER(_f)
     L.smk_set_solver.argtypes = [_vp, _i, _i, _i]
     L.smk_set_pass_ctas.argtypes = [_vp, _i]
+    L.smk_set_readback_box.argtypes = [_vp, _i]
     L.smk_last_pass_ctas.argtypes = [_vp]
     L.smk_set_obstacle_mode.argtypes = [_vp, _i]
     L.smk_read_density_half.argtypes = [_vp, _vp]
@@ -217,6 +218,7 @@ class SmokeSim:
     def set_solver(self, variant=0, iterations=30, fuse=0): self._ck(self.L.smk_set_solver(self.h, variant, iterations, fuse))
     def set_pass_ctas(self, nctas): self._ck(self.L.smk_set_pass_ctas(self.h, int(nctas)))
     def last_pass_ctas(self): return int(self.L.smk_last_pass_ctas(self.h))
+    def set_readback_box(self, on): self._ck(self.L.smk_set_readback_box(self.h, int(on)))
     def set_stream(self, cuda_stream): self._ck(self.L.smk_set_stream(self.h, cuda_stream))
 
     # -- the step (cu:774-819)

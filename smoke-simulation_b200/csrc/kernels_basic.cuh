@@ -10,6 +10,7 @@
 // project/smokeSimulation.cu; the pattern is restated at each function).  The compiler can therefore
 // neither contract nor re-associate anything, and results are bit-identical to the reference step.
 #pragma once
+#include <climits>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include "grid.h"
@@ -595,6 +596,43 @@ __global__ void __launch_bounds__(256) k_advect_smoke32(GridP g, const float* __
     const float bx = (float)(unsigned)(g.W - 1), by = (float)(unsigned)(g.H - 1), bz = (float)(unsigned)(g.D - 1);
     s1[x + y * g.W + zr * cpl] = sample_global32(s0, g.W, cpl, g.zlo, px, py, pz, .5f, .5f, .5f, bx, by, bz, zv, flag);
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Bounding box (in y and z; whole x rows) of the non-zero cells of a cell field: box4 = {y0, y1, z0, z1}, half-open,
+// initialised by k_box_init.  One warp per row (W % 4 == 0), grid-stride over the H * nz rows; a CTA folds its rows in
+// shared memory and issues four atomics.  Used by the sparse blocking readback (smk_api.cu, readback_box).
+__global__ void k_box_init(int* box4)
+{
+    box4[0] = INT_MAX; box4[1] = INT_MIN; box4[2] = INT_MAX; box4[3] = INT_MIN;
+}
+__global__ void __launch_bounds__(256) k_density_rows_box(const float* __restrict__ s, int W, int H, int nz, int z_first,
+                                                          int* __restrict__ box4)
+{
+    __shared__ int sb[4];
+    if (threadIdx.x == 0) { sb[0] = INT_MAX; sb[1] = INT_MIN; sb[2] = INT_MAX; sb[3] = INT_MIN; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const long long rows = (long long)H * nz;
+    for (long long r = warp; r < rows; r += nwarps) {
+        const float4* row = reinterpret_cast<const float4*>(s + r * W);
+        unsigned any = 0;
+        for (int i = lane; i < W / 4; i += 32) {
+            const float4 q = row[i];
+            any |= (__float_as_uint(q.x) | __float_as_uint(q.y) | __float_as_uint(q.z) | __float_as_uint(q.w)) << 1; // -0.0 counts as zero
+        }
+        if (__any_sync(0xffffffffu, any != 0) && lane == 0) {
+            const int z = (int)(r / H), y = (int)(r - (long long)z * H);
+            atomicMin(&sb[0], y); atomicMax(&sb[1], y + 1);
+            atomicMin(&sb[2], z + z_first); atomicMax(&sb[3], z + z_first + 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && sb[1] != INT_MIN) {
+        atomicMin(&box4[0], sb[0]); atomicMax(&box4[1], sb[1]);
+        atomicMin(&box4[2], sb[2]); atomicMax(&box4[3], sb[3]);
+    }
+}
+
 
 // the same kernel writing the new density ALSO into a 3-D surface (the renderer's GL_R32F texture mapped
 // through CUDA-GL interop, boundingBox.cpp:364-385) instead of going device -> host -> glTexSubImage3D (cu:814).  The

@@ -154,6 +154,14 @@ struct smk_sim {
     float* snapshot = nullptr;
     void* half_stage = nullptr; // binary16 staging buffer of smk_read_density_half
     bool copy_pending = false;
+    // sparse blocking readback (smk_set_readback_box / SMK_READBACK_BOX=1, single GPU): rows that can hold non-zero density only
+    bool box_mode = getenv("SMK_READBACK_BOX") && atoi(getenv("SMK_READBACK_BOX")) != 0;
+    int* d_box = nullptr;          // device {y0, y1, z0, z1} of the new density's non-zero rows
+    int* h_box = nullptr;          // pinned mirror, valid after the step's stream has been synchronised
+    int host_box[4] = {0, 0, 0, 0}; // non-zero rows of what the caller's buffer holds (after the last readback)
+    const float* host_box_buf = nullptr; // the buffer host_box describes (nullptr: unknown -> full copy)
+    float* box_pending_host = nullptr;   // readback whose box check is due at the next smk_sync
+    int box_copied[4] = {0, 0, 0, 0};    // rows copied by that readback (y0 >= y1: nothing, z0 < 0: everything)
 
     // timing
     std::vector<TimedSpan> spans;
@@ -1149,6 +1157,69 @@ int exchange_overlapped_with_advect(smk_sim* s, const slab::Op& adv, float dt, b
     return SMK_OK;
 }
 
+// Sparse blocking readback (opt-in, single GPU).  The density is exactly zero outside the plume, and non-zero density
+// moves at most (backtrace reach + 1) cells per step.  The caller's buffer is known to hold non-zero values only in the
+// rows `host_box` (what the previous readback found); so copying the rows grow(host_box, 2) leaves the buffer
+// bit-identical to a full copy PROVIDED the new density's non-zero rows lie inside them -- which a small reduction
+// kernel reports and smk_sync checks after the step; if not (a source moved, a long backtrace, first call, another
+// buffer), the full copy follows.  The reference always copies everything (cu:814).
+int readback_box(smk_sim* s, float* density_host)
+{
+    const GridP& g = s->g;
+    Span sp(s, SMK_STAGE_READBACK);
+    if (!s->d_box) {
+        CK(s, cudaMalloc(&s->d_box, 4 * sizeof(int)));
+        CK(s, cudaMallocHost(&s->h_box, 4 * sizeof(int)));
+    }
+    const float* src = s->smoke[s->past];
+    smk::k_box_init<<<1, 1, 0, s->stream>>>(s->d_box);
+    smk::k_density_rows_box<<<4 * s->num_sms, 256, 0, s->stream>>>(src, g.W, g.H, g.nzc, g.zlo, s->d_box);
+    s->launches += 2;
+    CK(s, cudaMemcpyAsync(s->h_box, s->d_box, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    const size_t bytes = (size_t)g.nzc * g.cplane * sizeof(float);
+    try_register(s, density_host, bytes);
+    int c[4] = {0, 0, -1, -1}; // default: everything
+    if (s->host_box_buf == density_host) {
+        const int G = 2;
+        if (s->host_box[0] >= s->host_box[1]) { c[0] = c[1] = c[2] = c[3] = 0; } // the buffer is all zero: copy nothing
+        else {
+            c[0] = std::max(0, s->host_box[0] - G); c[1] = std::min(g.H, s->host_box[1] + G);
+            c[2] = std::max(0, s->host_box[2] - G); c[3] = std::min(g.D, s->host_box[3] + G);
+            if ((double)(c[1] - c[0]) * (c[3] - c[2]) > 0.6 * (double)g.H * g.D) { c[0] = c[1] = 0; c[2] = c[3] = -1; } // not worth it
+        }
+    }
+    s->readback_bytes += c[2] < 0 ? bytes : (size_t)std::max(0, c[1] - c[0]) * g.W * 4 * (size_t)std::max(0, c[3] - c[2]);
+    if (c[2] < 0) {
+        CK(s, cudaMemcpyAsync(density_host, src, bytes, cudaMemcpyDeviceToHost, s->stream));
+    } else if (c[0] < c[1]) {
+        const size_t off = (size_t)c[2] * g.cplane + (size_t)c[0] * g.W;
+        CK(s, cudaMemcpy2DAsync(density_host + off, (size_t)g.cplane * 4, src + off, (size_t)g.cplane * 4,
+                                (size_t)(c[1] - c[0]) * g.W * 4, (size_t)(c[3] - c[2]), cudaMemcpyDeviceToHost, s->stream));
+    }
+    for (int i = 0; i < 4; i++) s->box_copied[i] = c[i];
+    s->box_pending_host = density_host;
+    return SMK_OK;
+}
+
+// after the step's stream has been synchronised: the new density's non-zero rows are known; complete the readback
+int finish_readback_box(smk_sim* s)
+{
+    float* host = s->box_pending_host;
+    s->box_pending_host = nullptr;
+    int e[4] = {s->h_box[0], s->h_box[1], s->h_box[2], s->h_box[3]};
+    if (e[1] == INT_MIN) { e[0] = e[1] = e[2] = e[3] = 0; } // all zero
+    const int* c = s->box_copied;
+    const bool covered = c[2] < 0 || e[0] >= e[1] || (c[0] < c[1] && e[0] >= c[0] && e[1] <= c[1] && e[2] >= c[2] && e[3] <= c[3]);
+    if (!covered) {
+        const GridP& g = s->g;
+        CK(s, cudaMemcpy(host, s->smoke[s->past], (size_t)g.nzc * g.cplane * sizeof(float), cudaMemcpyDeviceToHost));
+        s->readback_bytes += (size_t)g.nzc * g.cplane * sizeof(float);
+    }
+    for (int i = 0; i < 4; i++) s->host_box[i] = e[i];
+    s->host_box_buf = host;
+    return SMK_OK;
+}
+
 int enqueue_step(smk_sim* s, float dt, float* density_host, bool pipelined = false)
 {
     int rc = SMK_OK;
@@ -1158,7 +1229,8 @@ int enqueue_step(smk_sim* s, float dt, float* density_host, bool pipelined = fal
     // in z-chunks and every finished chunk starts its way to the host on the copy stream while the next one is
     // computed; the stream of the step then waits for the last copy.
     static const int split_n = getenv("SMK_READBACK_CHUNKS") ? atoi(getenv("SMK_READBACK_CHUNKS")) : 4;
-    const bool split = density_host && !pipelined && split_n > 1 && !ops.empty() && ops.back().kind == slab::OP_ADVECT_SMOKE &&
+    const bool boxed = s->box_mode && density_host && !pipelined && s->geom.world == 1 && (s->g.W & 3) == 0;
+    const bool split = !boxed && density_host && !pipelined && split_n > 1 && !ops.empty() && ops.back().kind == slab::OP_ADVECT_SMOKE &&
                        ops.back().b - ops.back().a >= 8 * split_n;
     const size_t nops = split ? ops.size() - 1 : ops.size();
     bool smoke_pulled = false;
@@ -1180,6 +1252,7 @@ int enqueue_step(smk_sim* s, float dt, float* density_host, bool pipelined = fal
         rc = exec_op(s, ops[i], dt);
     }
     if (rc) return rc;
+    if (boxed) return readback_box(s, density_host);
     if (split) {
         const GridP& g = s->g;
         const slab::Op& op = ops.back();
@@ -1579,6 +1652,8 @@ int smk_destroy(smk_sim* s)
     if (s->density_surf) cudaDestroySurfaceObject(s->density_surf);
     cudaFree(s->snapshot);
     cudaFree(s->half_stage);
+    cudaFree(s->d_box);
+    if (s->h_box) cudaFreeHost(s->h_box);
     while (!s->registered.empty()) drop_registration(s, s->registered.size() - 1);
     for (auto& sp : s->spans) { cudaEventDestroy(sp.e0); cudaEventDestroy(sp.e1); }
     for (auto e : s->free_events) cudaEventDestroy(e);
@@ -1672,6 +1747,14 @@ int smk_set_pass_ctas(smk_sim* s, int nctas)
 
 int smk_last_pass_ctas(smk_sim* s) { return s ? s->last_pass_ctas : -SMK_ERR_ARG; }
 
+int smk_set_readback_box(smk_sim* s, int on)
+{
+    if (!s) return SMK_ERR_ARG;
+    s->box_mode = on != 0;
+    s->host_box_buf = nullptr; // whatever the caller's buffer holds is unknown again
+    return SMK_OK;
+}
+
 int smk_set_stream(smk_sim* s, void* cuda_stream)
 { DeviceGuard dg(s);
     if (!s) return SMK_ERR_ARG;
@@ -1700,6 +1783,10 @@ int smk_sync(smk_sim* s)
     if (!s) return SMK_ERR_ARG;
     CK(s, cudaStreamSynchronize(s->stream));
     if (s->copy_pending) { CK(s, cudaStreamSynchronize(s->copy_stream)); s->copy_pending = false; }
+    if (s->box_pending_host) {
+        int rc = finish_readback_box(s);
+        if (rc) return rc;
+    }
     { // device-side error flags: [0] backtrace left the valid planes (slab runs), [1] peer wait timed out, [2] TMA timeout (any run)
         int flag[3] = {0, 0, 0};
         CK(s, cudaMemcpy(flag, s->d_flags, sizeof(flag), cudaMemcpyDeviceToHost));

@@ -193,3 +193,36 @@ def test_bit_packed_mask_round_trip_and_step(po, smk):
     compare(po, a, b, "bit-packed voxel mask")
     assert np.array_equal(np.unpackbits(a.get_mask_bits(), bitorder="little")[:W * H * D].reshape(D, H, W), vox)
     a.close()
+
+
+def test_sparse_readback_leaves_the_host_buffer_identical(po, smk):
+    """smk_set_readback_box: the caller's buffer after every step == the device density, through a growing plume, a
+    source that jumps (fallback to the full copy), an injected density, a switch to a second buffer and back, and the
+    copies get smaller than the field once the plume is known."""
+    W, H, D = 64, 96, 80
+    a = smk.SmokeSim(W, H, D)
+    a.set_params(-9.82, 15.0)
+    sid = a.add_source(32.0, 12.0, 40.0, 5.0)
+    a.add_obstacle(32.0, 40.0, 40.0, 0, 0, 0, 6.0)
+    a.set_readback_box(1)
+    h1 = np.full((D, H, W), 7.0, dtype=np.float32)   # garbage the first (full) copy must overwrite
+    h2 = np.full((D, H, W), -3.0, dtype=np.float32)
+    full = W * H * D * 4
+    small = 0
+    before = a.readback_bytes()
+    for t in range(40):
+        if t == 20:
+            a.update_object_pos(sid, 20.0, 70.0, 60.0)            # far outside the known rows
+        if t == 28:
+            rng = np.random.default_rng(1)
+            a.set_field(po.SMOKE, po.NOW, (rng.uniform(0, 1, (D, H, W)) < 0.001).astype(np.float32))
+        buf = h2 if 12 <= t < 16 else h1
+        a.step(po.tick_dt(t), buf)
+        assert np.array_equal(buf, a.get_field(po.SMOKE, po.PAST)), t
+        now = a.readback_bytes()
+        small += (now - before) < full
+        before = now
+    assert small >= 10
+    a.close()
+
+

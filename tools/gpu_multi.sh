@@ -5,9 +5,9 @@
 cd "$(dirname "$0")/.." || exit 1
 O=gpurun_out; T=${1:-mg}; N=${2:-2}; mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --master-port 29655 --nproc-per-node"
-timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -q > $O/${T}_pytest_multi.log 2>&1; echo "pytest multi rc=$?"; tail -3 $O/${T}_pytest_multi.log
+[ -z "$SKIP_PYTEST" ] && { timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -q > $O/${T}_pytest_multi.log 2>&1; echo "pytest multi rc=$?"; tail -3 $O/${T}_pytest_multi.log; }
 for dims in "64 48 40" "256 256 80"; do
-  timeout 300 $TR 2 tools/mp_check.py p2p $dims 2>&1 | grep -E "mp_check|MISMATCH" | tee -a $O/${T}_mp_check.log
+  timeout 300 $TR ${MPW:-2} tools/mp_check.py p2p $dims 2>&1 | grep -E "mp_check|MISMATCH" | tee -a $O/${T}_mp_check.log
 done
 # adaptive advection margin: a hitch tick (dt = 0.5, backtraces of ~3 planes) must stay bit-identical; dt = 16 (reach beyond the
 # ghost planes) must be reported as SMK_ERR_REACH by the slab ranks
