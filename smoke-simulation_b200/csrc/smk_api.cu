@@ -6,6 +6,7 @@
 // There is no CPU fallback anywhere in this file: if CUDA is unavailable every call fails with SMK_ERR_CUDA.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h> // header-only (NVTX v3): ranges per stage for Nsight Systems timelines
 
 #include <algorithm>
 #include <climits>
@@ -254,6 +255,8 @@ struct Span {
     TimedSpan sp;
     Span(smk_sim* s_, int stage) : s(s_)
     {
+        static const char* const names[SMK_STAGE_COUNT] = {"smk:fill", "smk:force+clamp", "smk:pressure", "smk:advect u,v,w", "smk:advect density", "smk:readback"};
+        nvtxRangePushA(names[stage]);
         sp.stage = stage;
         sp.e0 = get_event(s);
         sp.e1 = get_event(s);
@@ -263,6 +266,7 @@ struct Span {
     {
         cudaEventRecord(sp.e1, s->stream);
         s->spans.push_back(sp);
+        nvtxRangePop();
     }
 };
 
