@@ -242,6 +242,11 @@ int smk_debug_pass_ctas(smk_sim* s, long long* out4, int max_ctas);
 /* bytes the steps of this handle have copied device -> host so far (the density readback of cu:814; counted where the
  * copies are enqueued, so bench.py reports measured, not assumed, bytes per step) */
 unsigned long long smk_readback_bytes(smk_sim* s);
+/* Self-check of the pressure pass's binary32 evaluation of the over-relaxation product `(float)((double)q * -1.9)`
+ * (cu:384) against the double-precision sequence, on the device, for the `count` binary32 bit patterns from `first`
+ * (count = 2^32: all of them, ~1 s).  *mismatches must come back 0; *ties (may be NULL) = inputs resolved by the
+ * tie-to-even rule (kernels_pressure_tma.cuh, p_from_q; CPU twin: tools/experiments/omega_fp32_exhaustive.c). */
+int smk_selfcheck_omega(int device, unsigned first, unsigned long long count, unsigned long long* mismatches, unsigned long long* ties);
 
 /* ---- multi-GPU halo transport (slab mode) --------------------------------------------------------------- */
 /* Caller-provided exchange: called from smk_step when ghost planes of a field set must be refreshed.

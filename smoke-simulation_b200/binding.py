@@ -115,6 +115,7 @@ def load_library():
     L.smk_launch_count.restype = C.c_long
     L.smk_readback_bytes.argtypes = [_vp]
     L.smk_readback_bytes.restype = C.c_ulonglong
+    L.smk_selfcheck_omega.argtypes = [_i, C.c_uint, C.c_ulonglong, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     L.smk_set_exchange.argtypes = [_vp, EXCHANGE_FN, _vp]
     L.smk_exec_op.argtypes = [_vp, C.POINTER(_i), _f]
     L.smk_p2p_export.argtypes = [_vp, C.c_char_p]
@@ -130,6 +131,16 @@ def load_library():
     L.smk_last_error.restype = C.c_char_p
     _lib = L
     return L
+
+
+def selfcheck_omega(first=0, count=1 << 32, device=0):
+    """(mismatches, ties) of the binary32 over-relaxation product against the double-precision one, on the device."""
+    L = load_library()
+    bad, ties = C.c_ulonglong(0), C.c_ulonglong(0)
+    rc = L.smk_selfcheck_omega(device, first, count, C.byref(bad), C.byref(ties))
+    if rc != 0:
+        raise SmokeError(f"smk_selfcheck_omega failed: {rc}")
+    return int(bad.value), int(ties.value)
 
 
 def field_shape(field, W_, H_, D_):

@@ -137,11 +137,50 @@ __device__ __forceinline__ void sts32(unsigned a, float v)
 {
     asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(a), "n"(OFF), "f"(v) : "memory");
 }
-// p = (float)((double)q * -1.9) per half (cu:384; DMUL by the negated constant like the reference's SASS)
-__device__ __forceinline__ b64 p_from_q(b64 q)
+// p = (float)((double)q * -1.9) per half (cu:384; DMUL by the negated constant like the reference's SASS): the exact
+// sequence, 4 F2F + 2 DMUL.  F2F runs at 16 lanes/clk/SM and the three instructions sit in the middle of the dependent
+// chain of a sweep (~110-150 cycles measured): the sweeps use p_from_q below and keep this one for denormal-range inputs.
+__device__ __forceinline__ b64 p_from_q_f64(b64 q)
 {
     return pk(__double2float_rn(__dmul_rn((double)lo32(q), M19)), __double2float_rn(__dmul_rn((double)hi32(q), M19)));
 }
+// The same value in binary32 arithmetic, for q = 0 and |q| >= 2^-99 (tools/experiments/omega_fp32_exhaustive.c checks
+// all 2^32 inputs against the double product, zeros' signs included).  -1.9 (binary64) = ch + cl + ...;
+//     P+ = fma(q, ch, q * (cl + 2^-39)),   P- = fma(q, ch, q * (cl - 2^-39))
+// bracket the doubly rounded product: if they agree that is the answer.  If not, a binary32 rounding boundary lies within
+// 2^-40 |p| of the product; 19 q / 10 lives on a lattice of tenths of an ulp, so it is an exact tie of 19 q / 10, the
+// binary64 product (off by 8.9e-17 relative, less than half an ulp of binary64) rounds ONTO the midpoint and the
+// conversion breaks the tie to even: take the even one of the two adjacent values.  No branch, no F2F, no DMUL.
+__device__ __forceinline__ unsigned even_of(unsigned bp, unsigned bm)
+{
+    return max(bp, bm) & ~((bp - bm) & 1u); // equal: that value; adjacent bit patterns: the larger one with bit 0 cleared if set... i.e. the even one
+}
+__device__ __forceinline__ b64 p_from_q(b64 q)
+{
+    const b64 CH = pk(-0x1.e66666p+0f, -0x1.e66666p+0f), CLP = pk(-0x1.99919ap-26f, -0x1.99919ap-26f), CLM = pk(-0x1.99a19ap-26f, -0x1.99a19ap-26f);
+    const b64 pp = ffma2(q, CH, fmul2(q, CLP)), pm = ffma2(q, CH, fmul2(q, CLM));
+    return pk(__uint_as_float(even_of(__float_as_uint(lo32(pp)), __float_as_uint(lo32(pm)))),
+              __uint_as_float(even_of(__float_as_uint(hi32(pp)), __float_as_uint(hi32(pm)))));
+}
+// self-check (smk_selfcheck_omega): every binary32 q of [first, first + count) through both evaluations on the device
+__global__ void k_omega_check(unsigned first, unsigned long long count, unsigned long long* __restrict__ out)
+{
+    unsigned long long bad = 0, ties = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < count; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned b = first + (unsigned)i, a = b & 0x7fffffffu;
+        if (a >= 0x7f800000u || (a != 0u && a < 0x0E000000u)) continue; // inf / nan; 0 < |q| < 2^-99 never reaches p_from_q
+        const float q = __uint_as_float(b);
+        const b64 q2 = pk(q, -q), fast = p_from_q(q2), ref = p_from_q_f64(q2);
+        bad += (fast != ref);
+        const b64 CH = pk(-0x1.e66666p+0f, -0x1.e66666p+0f), CLP = pk(-0x1.99919ap-26f, -0x1.99919ap-26f), CLM = pk(-0x1.99a19ap-26f, -0x1.99a19ap-26f);
+        ties += (ffma2(q2, CH, fmul2(q2, CLP)) != ffma2(q2, CH, fmul2(q2, CLM)));
+    }
+    if (bad) atomicAdd(out, bad);
+    if (ties) atomicAdd(out + 1, ties);
+}
+
+// |d| below this (and d != 0) takes the slow path: exact integer quotient below 2^-125 (div6_tiny), F2F/DMUL product
+constexpr unsigned TINY_D = 0x0F7FFFFFu; // bits(2^-96) - 1: with n <= 6 neighbours |q| = |d / n| >= 2^-99 above it
 
 // bounded mbarrier wait, not unrolled (the first probe almost always succeeds: the loads run NS-1 planes ahead)
 __device__ __forceinline__ bool mbar_wait1(unsigned long long* bar, unsigned parity)
@@ -164,6 +203,16 @@ __device__ __forceinline__ b64 fix_tiny_q(b64 q, b64 d, unsigned ax, unsigned ay
     if (six_lo && ax < 0x00ffffffu) qx = div6_tiny(lo32(d));
     if (six_hi && ay < 0x00ffffffu) qy = div6_tiny(hi32(d));
     return pk(qx, qy);
+}
+// the denormal-range path of a sweep: exact quotient where the correction sequence can miss, double-precision product
+#ifndef SMK_SLOW_P_INLINE
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+b64 slow_p(b64 q, b64 d, unsigned ax, unsigned ay, bool six_lo, bool six_hi)
+{
+    return p_from_q_f64(fix_tiny_q(q, d, ax, ay, six_lo, six_hi));
 }
 
 // ---- rare paths, out of line (they cost a call only where they are taken) ---------------------------------------------
@@ -214,10 +263,16 @@ __device__ __forceinline__ b64 pk(float2 v) { return pk(v.x, v.y); }
 // (the parity offset is an immediate).  Pairs: E = (f[4h], f[4h+2]), O = (f[4h+1], f[4h+3]).
 // GENERAL = false: the CTA's planes hold no COMPLEX cell (flags written with the stencil codes, grid.h) -- the general
 // update is not even compiled in, so the hot path has no control-flow merge for the compiler to resolve with copies.
+#ifdef SMK_TRACE_FINE
+#define FT(k) do { if (ft) ft[k] = clock64(); } while (0)
+#else
+#define FT(k) do { } while (0)
+#endif
 template <int PAR, bool GENERAL>
 __device__ __forceinline__ void tma_update(b64& ue, b64& uo, b64& we, b64& wo, b64& we1, b64& wo1, const unsigned a, const unsigned cw,
-                                           const bool hnz)
+                                           const bool hnz, long long* ft = nullptr)
 {
+    FT(0);
     constexpr unsigned FULL = 0xffffffffu;
     constexpr unsigned SH = 8u * PAR;                 // byte 0/2 (PAR 0) or 1/3 (PAR 1) of the code word
     constexpr unsigned M_AC = 0x00C000C0u << SH;      // ACTIVE | COMPLEX of both cells
@@ -236,6 +291,7 @@ __device__ __forceinline__ void tma_update(b64& ue, b64& uo, b64& we, b64& wo, b
     d = fadd2(d, V1);                    //  ... + v1
     d = ffma2(W0, M1, d);                //  ... - w0
     d = fadd2(d, W1);                    //  ... + w1
+    FT(1);
 
     // tier A: both cells of every lane ACTIVE with six fluid neighbours; tier B: no COMPLEX cell (some are not updated)
     const bool allact = __all_sync(FULL, (cw & M_AC) == V_A);
@@ -244,10 +300,14 @@ __device__ __forceinline__ void tma_update(b64& ue, b64& uo, b64& we, b64& wo, b
         const b64 q0 = fmul2(d, R6);
         const b64 rem = ffma2(q0, M6, d);
         b64 q = ffma2(rem, R6, q0);
+        FT(2);
         // below 2^-125 (and d != 0) a tie on the denormal grid can round the wrong way -> exact integer quotient
         const unsigned ax = (__float_as_uint(lo32(d)) & 0x7fffffffu) - 1u, ay = (__float_as_uint(hi32(d)) & 0x7fffffffu) - 1u;
-        if (__any_sync(FULL, min(ax, ay) < 0x00ffffffu)) q = fix_tiny_q(q, d, ax, ay);
-        b64 P = p_from_q(q);
+        b64 P;
+        if (__any_sync(FULL, min(ax, ay) < TINY_D)) { P = slow_p(q, d, ax, ay, true, true); FT(5); }
+        else P = p_from_q(q);
+        FT(6);
+        FT(3);
         if (!allact) // cells that are not ACTIVE get P = 0 (old -/+ 0 = old)
             P = pk((cw & (0x40u << SH)) ? lo32(P) : 0.f, (cw & (0x400000u << SH)) ? hi32(P) : 0.f);
         U0 = ffma2(P, M1, U0); U1 = fadd2(U1, P);
@@ -265,8 +325,9 @@ __device__ __forceinline__ void tma_update(b64& ue, b64& uo, b64& we, b64& wo, b
         const b64 rem = ffma2(q0, MN, d);
         b64 q = ffma2(rem, RR2, q0);
         const unsigned ax = (__float_as_uint(lo32(d)) & 0x7fffffffu) - 1u, ay = (__float_as_uint(hi32(d)) & 0x7fffffffu) - 1u;
-        if (__any_sync(FULL, min(ax, ay) < 0x00ffffffu)) q = fix_tiny_q(q, d, ax, ay, !fa_, !fb_);
-        b64 P = p_from_q(q);
+        b64 P;
+        if (__any_sync(FULL, min(ax, ay) < TINY_D)) P = slow_p(q, d, ax, ay, !fa_, !fb_);
+        else P = p_from_q(q);
         if (!allact) P = pk((cw & (0x40u << SH)) ? lo32(P) : 0.f, (cw & (0x400000u << SH)) ? hi32(P) : 0.f);
         const b64 Pv0 = pk(fa_ ? 0.f : lo32(P), fb_ ? 0.f : hi32(P));
         U0 = ffma2(P, M1, U0); U1 = fadd2(U1, P);
@@ -286,6 +347,7 @@ __device__ __forceinline__ void tma_update(b64& ue, b64& uo, b64& we, b64& wo, b
         const float from_left = __shfl_up_sync(FULL, hi32(U1), 1); // the left quad's updated u[4h]
         ue = pk(hnz ? from_left : lo32(ue), lo32(U1));              // h == 0: tile edge, face stays stale (halo)
     }
+    FT(4);
 }
 
 __device__ __forceinline__ void force_clamp_node_pc(float& u, float& v, float& w, unsigned pc, float d, bool clampable, const ForceArgs& fa)
@@ -313,7 +375,11 @@ __device__ __forceinline__ void tma_issue_plane(const IssueArgs& q, int z, int s
     else if (q.has_hi && z > q.own_hi) { src = 2; zr = z - q.hi_zlo; }
     const CUtensorMap* ms = &q.maps->smoke[src];
     unsigned char* dst = q.stage + slot * C::SLOT;
+#ifdef SMK_PASS_TRACE
     long long* tr = (q.trace && z - q.t0 < 80 && z >= q.t0) ? q.trace + 16 * 80 * 8 + (z - q.t0) * 8 : nullptr;
+#else
+    long long* const tr = nullptr;
+#endif
     if (tr) tr[0] = clock64();
     mbar_expect_tx(&q.bars[slot], 3u * C::FB + (unsigned)(C::KW * C::LY) + (FORCE ? (unsigned)C::FB : 0u));
     if (tr) tr[1] = clock64();
@@ -450,10 +516,14 @@ __device__ __forceinline__ void tma_pass_piece(const GridP& g, const PassMaps& m
     // step and WAITS just before the first sweep of the next one.  What lies in between -- writing out u and w, the
     // producer's TMA issue, entering the next plane -- overlaps the skew between the warps instead of following it.
     // development aid: timestamps of three warps of one CTA (tools/cta_times.py trace)
+#ifdef SMK_PASS_TRACE // (make EXTRA=-DSMK_PASS_TRACE: the timestamps cost code size in every unrolled step)
 #define TRACE(k)                                                                                              \
     do {                                                                                                      \
         if (trace && lane == 0 && (t - t0) < 80) trace[((wid * 80) + (t - t0)) * 8 + (k)] = clock64();         \
     } while (0)
+#else
+#define TRACE(k) do { } while (0)
+#endif
     unsigned long long* const sbar = bars + NS;
     unsigned sph = 0;
     auto step_arrive = [&]() { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sbar)) : "memory"); };
@@ -465,8 +535,8 @@ __device__ __forceinline__ void tma_pass_piece(const GridP& g, const PassMaps& m
 
     // One z-step at rotation ROT (compile time): position k (plane t-k, k = -1 .. K) is ring entry (ROT - k) mod RR, and
     // the colour parity of the step is ROT & 1.  Returns false when the piece is finished (or a TMA transaction was lost).
-    auto step = [&](auto rot_c) -> bool {
-        constexpr int ROT = decltype(rot_c)::value, PAR = ROT & 1;
+    auto step = [&](auto rot_c, auto par_c) -> bool {
+        constexpr int ROT = decltype(rot_c)::value, PAR = decltype(par_c)::value;
         auto ph_of = [](int k) { return ((ROT - k) % RR + RR) % RR; };
         // every row has finished the sweeps of step t-1 (and entered plane t)
         if (!step_wait()) return false;
@@ -495,7 +565,13 @@ __device__ __forceinline__ void tma_pass_piece(const GridP& g, const PassMaps& m
         for (int j = 1; j <= K; j++) {
             if (j <= nsw)
                 tma_update<PAR, GENERAL>(UE[ph_of(j)], UO[ph_of(j)], WE[ph_of(j)], WO[ph_of(j)], WE[ph_of(j - 1)], WO[ph_of(j - 1)],
-                                         ((tt - (unsigned)j * C::RING_SLOT) & sw_mask) | sw_base, CW[ph_of(j)], hnz);
+                                         ((tt - (unsigned)j * C::RING_SLOT) & sw_mask) | sw_base, CW[ph_of(j)], hnz,
+#ifdef SMK_TRACE_FINE
+                                         (j == 2 && trace && lane == 0 && (t - t0) < 80) ? trace + 17 * 80 * 8 + ((wid * 80) + (t - t0)) * 8 : nullptr
+#else
+                                         nullptr
+#endif
+                );
             TRACE(3 + j);
             if (j == 1) { // (a) v of plane t-K-1 became final with the previous step: write it out (off the critical path)
                 const int s2 = t - K - 1;
@@ -540,16 +616,38 @@ __device__ __forceinline__ void tma_pass_piece(const GridP& g, const PassMaps& m
         if (!ok) return;
         step_arrive();   // plane t0 is in: counts as "step t0 - 1 done" for the first wait
     }
-    bool skip0 = c1;
-    for (;;) {
-        if (!skip0) { if (!step(std::integral_constant<int, 0>{})) break; }
-        skip0 = false;
-        if (!step(std::integral_constant<int, 1>{})) break;
-        if (!step(std::integral_constant<int, 2 % RR>{})) break;
-        if (!step(std::integral_constant<int, 3 % RR>{})) break;
-        if (RR > 4) {
-            if (!step(std::integral_constant<int, 4 % RR>{})) break;
-            if (!step(std::integral_constant<int, 5 % RR>{})) break;
+    using I0 = std::integral_constant<int, 0>;
+    using I1 = std::integral_constant<int, 1>;
+    if (GENERAL) {
+        // Tiles with COMPLEX cells (the floor row of every scene, obstacle surfaces): every tier of the update is compiled in,
+        // so the step body is large -- unrolled six times it no longer fits the instruction cache, and the traces showed every
+        // vote / branch of the hot tier paying an instruction fetch (2.2x per sweep).  Compact code instead: one step body per
+        // colour parity, plane t0 in ring entry 0, and the ring shifted by register moves after every step.
+        if (c1) { // the prologue put plane t0 into entry 1
+            UE[0] = UE[1]; UO[0] = UO[1]; WE[0] = WE[1]; WO[0] = WO[1]; CW[0] = CW[1];
+        }
+        for (;;) {
+            const bool go = ((rowpar + t) & 1) ? step(I0{}, I1{}) : step(I0{}, I0{});
+            if (!go) break;
+            // position k of the next step = position k-1 of this one; with ROT = 0 position k is entry (RR - k) % RR
+#pragma unroll
+            for (int k = K; k >= 0; k--) {
+                const int to = (RR - k) % RR, from = (RR - (k - 1)) % RR;
+                UE[to] = UE[from]; UO[to] = UO[from]; WE[to] = WE[from]; WO[to] = WO[from]; CW[to] = CW[from];
+            }
+        }
+    } else {
+        bool skip0 = c1;
+        for (;;) {
+            if (!skip0) { if (!step(I0{}, I0{})) break; }
+            skip0 = false;
+            if (!step(I1{}, I1{})) break;
+            if (!step(std::integral_constant<int, 2 % RR>{}, I0{})) break;
+            if (!step(std::integral_constant<int, 3 % RR>{}, I1{})) break;
+            if (RR > 4) {
+                if (!step(std::integral_constant<int, 4 % RR>{}, I0{})) break;
+                if (!step(std::integral_constant<int, 5 % RR>{}, I1{})) break;
+            }
         }
     }
     if (failed) return;
@@ -574,11 +672,20 @@ k_pressure_tma(GridP g, const __grid_constant__ PassMaps maps, float* __restrict
         return;
     }
 
-    int chunk = pr.chunk_first + (int)blockIdx.z * pr.chunk_step;
+    // CTAs are dispatched in linear block order and a piece of the bottom tile row (the floor: COMPLEX cells, the
+    // slower variant) takes ~1.5x as long as the others: hand those out first, so that they never form the tail.
+    int bx = (int)blockIdx.x, by = (int)blockIdx.y, bz = (int)blockIdx.z;
+    if (pr.sync.nchunks == 0 && gridDim.y > 1) {
+        const int gx = (int)gridDim.x, gy = (int)gridDim.y, gz = (int)gridDim.z;
+        int L = bx + gx * (by + gy * bz);
+        if (L < gx * gz) { by = 0; bx = L % gx; bz = L / gx; }
+        else { L -= gx * gz; bx = L % gx; L /= gx; by = 1 + L % (gy - 1); bz = L / (gy - 1); }
+    }
+    int chunk = pr.chunk_first + bz * pr.chunk_step;
     int bside = -1; // this CTA reads / serves the neighbour on that side (PassSync, kernels_pressure_reg.cuh)
     if (pr.sync.nchunks > 0) {
-        if (pr.sync.first) chunk = blockIdx.z == 0 ? 0 : blockIdx.z == 1 ? pr.sync.nchunks - 1 : (int)blockIdx.z - 1;
-        else chunk = (int)blockIdx.z + 1 < pr.sync.nchunks ? (int)blockIdx.z + 1 : 0; // boundary chunks last
+        if (pr.sync.first) chunk = bz == 0 ? 0 : bz == 1 ? pr.sync.nchunks - 1 : bz - 1;
+        else chunk = bz + 1 < pr.sync.nchunks ? bz + 1 : 0; // boundary chunks last
         if (chunk == 0 && pr.sync.wait_ctr[0]) bside = 0;
         else if (chunk == pr.sync.nchunks - 1 && pr.sync.wait_ctr[1]) bside = 1;
         if (bside >= 0) {
@@ -606,18 +713,18 @@ k_pressure_tma(GridP g, const __grid_constant__ PassMaps maps, float* __restrict
         if (K == 4 && cflag) {
             cx = 0;
             const int za = max(zo0 - K, g.zlo), zb = min(zo1 + K - 1, g.zlo + g.nzc - 1);
-            const int per = (int)(gridDim.x * gridDim.y), me = (int)(blockIdx.y * gridDim.x + blockIdx.x);
+            const int per = (int)(gridDim.x * gridDim.y), me = by * (int)gridDim.x + bx;
             for (int z = za + (int)threadIdx.x; z <= zb; z += (int)blockDim.x) cx |= cflag[(long long)(z - g.zlo) * per + me];
             cx = __syncthreads_or(cx);
         }
-        if (cx) tma_pass_piece<K, NW, FORCE, MAXW, true>(g, maps, uo, vo, wo, sweep0, pr, fa, smem_raw, (int)blockIdx.x, (int)blockIdx.y, zo0, zo1, wmax, flags,
-                                                         (dbg && blockIdx.x == dbg[(1 << 17) - 3] && blockIdx.y == dbg[(1 << 17) - 2] && blockIdx.z == dbg[(1 << 17) - 1]) ? dbg + (1 << 17) : nullptr);
-        else tma_pass_piece<K, NW, FORCE, MAXW, false>(g, maps, uo, vo, wo, sweep0, pr, fa, smem_raw, (int)blockIdx.x, (int)blockIdx.y, zo0, zo1, wmax, flags,
-                                                       (dbg && blockIdx.x == dbg[(1 << 17) - 3] && blockIdx.y == dbg[(1 << 17) - 2] && blockIdx.z == dbg[(1 << 17) - 1]) ? dbg + (1 << 17) : nullptr);
+        if (cx) tma_pass_piece<K, NW, FORCE, MAXW, true>(g, maps, uo, vo, wo, sweep0, pr, fa, smem_raw, bx, by, zo0, zo1, wmax, flags,
+                                                         (dbg && bx == dbg[(1 << 17) - 3] && by == dbg[(1 << 17) - 2] && bz == dbg[(1 << 17) - 1]) ? dbg + (1 << 17) : nullptr);
+        else tma_pass_piece<K, NW, FORCE, MAXW, false>(g, maps, uo, vo, wo, sweep0, pr, fa, smem_raw, bx, by, zo0, zo1, wmax, flags,
+                                                       (dbg && bx == dbg[(1 << 17) - 3] && by == dbg[(1 << 17) - 2] && bz == dbg[(1 << 17) - 1]) ? dbg + (1 << 17) : nullptr);
         if (dbg && threadIdx.x == 0) { // development aid (SMK_PASS_DEBUG): per-CTA start, duration, SM and variant
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            long long* o = dbg + 4 * ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+            long long* o = dbg + 4 * ((long long)(bz * (int)gridDim.y + by) * (int)gridDim.x + bx);
             o[0] = dbg_t0; o[1] = clock64() - dbg_t0; o[2] = smid; o[3] = cx * 1000 + (zo1 - zo0);
         }
     }

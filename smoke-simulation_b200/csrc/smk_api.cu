@@ -639,6 +639,8 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
     const int nz = out_hi - out_lo;
     const int tx = (g.W + 1 + C::OX - 1) / C::OX, ty = (g.SY + C::OY - 1) / C::OY;
     int zchunk = pick_zchunk(s, tx * ty, K, nz);
+    static const int force_chunks = getenv("SMK_PASS_NCHUNKS") ? atoi(getenv("SMK_PASS_NCHUNKS")) : 0; // experiments
+    if (force_chunks > 0) zchunk = std::max(K, (nz + force_chunks - 1) / force_chunks);
     // the lean kernel addresses a chunk with 32-bit byte offsets: (planes of a chunk incl. lead-in) x plane bytes < 2^32
     while ((long long)(zchunk + 2 * K + 2) * g.nplane * 4 >= (1ll << 32) && zchunk > 2 * K) zchunk = (zchunk + 1) / 2;
     // Only the first and the last z-chunk may touch planes within K of the slab ends (the neighbours read those / they
@@ -2150,14 +2152,34 @@ int smk_debug_pass_ctas(smk_sim* s, long long* out4, int max_ctas)
     DeviceGuard dg(s);
     if (!s->d_passdbg) return 0;
     if (max_ctas < 0) { // trace region: 16 warps x 80 steps x 4 timestamps of one CTA
-        if (cudaStreamSynchronize(s->stream) != cudaSuccess || cudaMemcpy(out4, s->d_passdbg + (1 << 17), (size_t)17 * 80 * 8 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -SMK_ERR_CUDA;
-        return 17 * 80;
+        if (cudaStreamSynchronize(s->stream) != cudaSuccess || cudaMemcpy(out4, s->d_passdbg + (1 << 17), (size_t)34 * 80 * 8 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -SMK_ERR_CUDA;
+        return 34 * 80;
     }
     const int n = std::min(max_ctas, std::min(s->passdbg_ctas, 4096));
     if (cudaStreamSynchronize(s->stream) != cudaSuccess || cudaMemcpy(out4, s->d_passdbg, (size_t)n * 32, cudaMemcpyDeviceToHost) != cudaSuccess) return -SMK_ERR_CUDA;
     return n;
 }
 unsigned long long smk_readback_bytes(smk_sim* s) { return s ? s->readback_bytes : 0; }
+
+int smk_selfcheck_omega(int device, unsigned first, unsigned long long count, unsigned long long* mismatches, unsigned long long* ties)
+{
+    if (!mismatches || count > (1ull << 32)) return SMK_ERR_ARG;
+    int prev = 0;
+    if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) return SMK_ERR_CUDA;
+    unsigned long long* d = nullptr;
+    unsigned long long h[2] = {0, 0};
+    int rc = SMK_OK;
+    if (cudaMalloc(&d, 16) != cudaSuccess || cudaMemset(d, 0, 16) != cudaSuccess) rc = SMK_ERR_CUDA;
+    if (rc == SMK_OK) {
+        smk::k_omega_check<<<148 * 8, 256>>>(first, count, d);
+        if (cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost) != cudaSuccess) rc = SMK_ERR_CUDA;
+    }
+    cudaFree(d);
+    cudaSetDevice(prev);
+    *mismatches = h[0];
+    if (ties) *ties = h[1];
+    return rc;
+}
 
 int smk_set_exchange(smk_sim* s, smk_exchange_fn fn, void* ctx)
 {

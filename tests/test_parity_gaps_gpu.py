@@ -226,3 +226,13 @@ def test_sparse_readback_leaves_the_host_buffer_identical(po, smk):
     a.close()
 
 
+
+
+def test_omega_product_in_binary32_equals_the_double_product_for_every_input(smk):
+    """The TMA-staged pressure pass evaluates `(float)((double)q * -1.9)` (cu:384) with four packed binary32 operations and
+    a tie-to-even select instead of F2F / DMUL / F2F.  Every one of the 2^32 bit patterns (inf / nan and the denormal-range
+    band that never reaches it excluded) through both on the device: zero mismatches, and the tie rule must actually fire
+    (1/19 of the inputs are exact ties of 19 q / 10)."""
+    bad, ties = smk.selfcheck_omega()
+    assert bad == 0
+    assert 190_000_000 < ties // 2 < 210_000_000   # the kernel checks q and -q per pattern

@@ -37,7 +37,7 @@ if len(late): print(f"  second-wave starts: first {late[0]}, last {late[-1]}")
 
 # ---- per-step trace of one lean CTA (tile (1,2), chunk 1): lane 0 of every warp stamps clock64 after the step barrier
 # wait + TMA issue (0), after its sweeps (1) and at the end of the step (2)
-tr = np.zeros((17, 80, 8), dtype=np.int64)
+tr = np.zeros((34, 80, 8), dtype=np.int64)
 if L.smk_debug_pass_ctas(sim.h, tr.ctypes.data_as(C.c_void_p), -1) > 0 and tr[5, 20, 0] > 0:
     steps = range(20, 50)
     for w in (0, 3, 5, 10, 15):
@@ -72,3 +72,12 @@ if L.smk_debug_pass_ctas(sim.h, tr.ctypes.data_as(C.c_void_p), -1) > 0 and tr[5,
             seg = np.median(np.diff(tr[w, 24:50, [0, 4, 5, 6, 7]].T, axis=1), axis=0)
             print(f"  warp {w}: start->sweep1 {seg[0]:.0f}, sweep2 {seg[1]:.0f}, sweep3 {seg[2]:.0f}, sweep4 {seg[3]:.0f}")
 
+
+    if os.environ.get("TRACE_FINE"):
+        ft = tr[17:33]
+        for w in (5, 6, 7, 8, 9, 10):
+            seg = ft[w, 24:50]
+            ok = seg[:, 4] > 0
+            if ok.any():
+                d = seg[ok]
+                print(f"  warp {w} sweep 2: loads+div {np.median(d[:,1]-d[:,0]):.0f}  q {np.median(d[:,2]-d[:,1]):.0f}  tiny check(+fix) {np.median(d[:,6]-d[:,2]):.0f}  P=f(q) {np.median(d[:,3]-d[:,6]):.0f}  updates+sts {np.median(d[:,4]-d[:,3]):.0f}  tiny fixes {int((d[:,5]>0).sum())}/{len(d)}")
