@@ -11,6 +11,6 @@ the repository root points its ``__path__`` here).
 """
 from . import scenes, slab  # noqa: F401
 from .binding import (  # noqa: F401
-    LIB_PATH, SmokeSim, SmokeError, load_library, build_library, declared_symbols,
+    LIB_PATH, SmokeSim, SmokeError, load_library, build_library, declared_symbols, selfcheck_omega,
     SMOKE, U, V, W, MASK, NOW, PAST, BUF0, BUF1,
 )

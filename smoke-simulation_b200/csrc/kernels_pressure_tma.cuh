@@ -153,7 +153,7 @@ __device__ __forceinline__ b64 p_from_q_f64(b64 q)
 // conversion breaks the tie to even: take the even one of the two adjacent values.  No branch, no F2F, no DMUL.
 __device__ __forceinline__ unsigned even_of(unsigned bp, unsigned bm)
 {
-    return max(bp, bm) & ~((bp - bm) & 1u); // equal: that value; adjacent bit patterns: the larger one with bit 0 cleared if set... i.e. the even one
+    return (bp & 1u) == 0u ? bp : bm; // equal: that value; adjacent bit patterns: exactly one of them is even
 }
 __device__ __forceinline__ b64 p_from_q(b64 q)
 {
@@ -179,8 +179,11 @@ __global__ void k_omega_check(unsigned first, unsigned long long count, unsigned
     if (ties) atomicAdd(out + 1, ties);
 }
 
-// |d| below this (and d != 0) takes the slow path: exact integer quotient below 2^-125 (div6_tiny), F2F/DMUL product
-constexpr unsigned TINY_D = 0x0F7FFFFFu; // bits(2^-96) - 1: with n <= 6 neighbours |q| = |d / n| >= 2^-99 above it
+// 0 < |d| < 2^-96 takes the slow path: exact integer quotient below 2^-125 (div6_tiny), F2F/DMUL product.  With n <= 6
+// neighbours |q| = |d / n| >= 2^-99 above it.  Key of a value: 2 * bits - 2 (mod 2^32: the sign falls out, zero wraps to
+// the top) -- one multiply-add per value; tiny  <=>  key < TINY_D.
+__device__ __forceinline__ unsigned tiny_key(float d) { return __float_as_uint(d) * 2u - 2u; }
+constexpr unsigned TINY_D = 2u * 0x0F800000u - 2u;
 
 // bounded mbarrier wait, not unrolled (the first probe almost always succeeds: the loads run NS-1 planes ahead)
 __device__ __forceinline__ bool mbar_wait1(unsigned long long* bar, unsigned parity)
@@ -210,8 +213,9 @@ __device__ __noinline__
 #else
 __device__ __forceinline__
 #endif
-b64 slow_p(b64 q, b64 d, unsigned ax, unsigned ay, bool six_lo, bool six_hi)
+b64 slow_p(b64 q, b64 d, bool six_lo, bool six_hi)
 {
+    const unsigned ax = (__float_as_uint(lo32(d)) & 0x7fffffffu) - 1u, ay = (__float_as_uint(hi32(d)) & 0x7fffffffu) - 1u;
     return p_from_q_f64(fix_tiny_q(q, d, ax, ay, six_lo, six_hi));
 }
 
@@ -302,9 +306,9 @@ __device__ __forceinline__ void tma_update(b64& ue, b64& uo, b64& we, b64& wo, b
         b64 q = ffma2(rem, R6, q0);
         FT(2);
         // below 2^-125 (and d != 0) a tie on the denormal grid can round the wrong way -> exact integer quotient
-        const unsigned ax = (__float_as_uint(lo32(d)) & 0x7fffffffu) - 1u, ay = (__float_as_uint(hi32(d)) & 0x7fffffffu) - 1u;
+        const unsigned ax = tiny_key(lo32(d)), ay = tiny_key(hi32(d));
         b64 P;
-        if (__any_sync(FULL, min(ax, ay) < TINY_D)) { P = slow_p(q, d, ax, ay, true, true); FT(5); }
+        if (__any_sync(FULL, min(ax, ay) < TINY_D)) { P = slow_p(q, d, true, true); FT(5); }
         else P = p_from_q(q);
         FT(6);
         FT(3);
@@ -324,9 +328,9 @@ __device__ __forceinline__ void tma_update(b64& ue, b64& uo, b64& we, b64& wo, b
         const b64 q0 = fmul2(d, RR2);
         const b64 rem = ffma2(q0, MN, d);
         b64 q = ffma2(rem, RR2, q0);
-        const unsigned ax = (__float_as_uint(lo32(d)) & 0x7fffffffu) - 1u, ay = (__float_as_uint(hi32(d)) & 0x7fffffffu) - 1u;
+        const unsigned ax = tiny_key(lo32(d)), ay = tiny_key(hi32(d));
         b64 P;
-        if (__any_sync(FULL, min(ax, ay) < TINY_D)) P = slow_p(q, d, ax, ay, !fa_, !fb_);
+        if (__any_sync(FULL, min(ax, ay) < TINY_D)) P = slow_p(q, d, !fa_, !fb_);
         else P = p_from_q(q);
         if (!allact) P = pk((cw & (0x40u << SH)) ? lo32(P) : 0.f, (cw & (0x400000u << SH)) ? hi32(P) : 0.f);
         const b64 Pv0 = pk(fa_ ? 0.f : lo32(P), fb_ ? 0.f : hi32(P));
@@ -476,9 +480,10 @@ __device__ __forceinline__ void tma_pass_piece(const GridP& g, const PassMaps& m
 
     // output: running pointers to this lane's quad in plane t-K (u, w) and t-K-1 (v)
     const long long o0 = (long long)(t0 - K - g.zlo) * g.nplane + (nok ? xg + yg * g.P : 0);
-    float* pou = uo + o0;
-    float* pow_ = wo + o0;
-    float* pov = vo + (o0 - g.nplane);
+    long long oo = o0;           // (one running offset, not three running pointers: registers)
+#define pou (uo + oo)
+#define pow_ (wo + oo)
+#define pov (vo + (oo - g.nplane))
     float wm = 0.f;
 
     unsigned tt = 0;            // (t - t0) << 13: slot bits of plane t in the v ring (masked)
@@ -582,6 +587,7 @@ __device__ __forceinline__ void tma_pass_piece(const GridP& g, const PassMaps& m
                 }
             }
         }
+    
         // (e) this thread's v faces of step t are written
         TRACE(1);
         step_arrive();
@@ -594,7 +600,7 @@ __device__ __forceinline__ void tma_pass_piece(const GridP& g, const PassMaps& m
                 *reinterpret_cast<float4*>(pow_) = make_float4(lo32(we), lo32(wq), hi32(we), hi32(wq));
                 if (MAXW) wm = fmaxf(fmaxf(fmaxf(wm, fabsf(lo32(we))), fmaxf(fabsf(lo32(wq)), fabsf(hi32(we)))), fabsf(hi32(wq)));
             }
-            pou += g.nplane; pow_ += g.nplane; pov += g.nplane;
+            oo += g.nplane;
         }
         // (b) plane t+1 enters (its staging slot was filled NS-1 steps ago): registers + v ring.  Its v stores are
         //     ordered before this thread's NEXT arrive, which is what the rows that read them (step t+2) wait for.
@@ -627,6 +633,7 @@ __device__ __forceinline__ void tma_pass_piece(const GridP& g, const PassMaps& m
             UE[0] = UE[1]; UO[0] = UO[1]; WE[0] = WE[1]; WO[0] = WO[1]; CW[0] = CW[1];
         }
         for (;;) {
+            t = __shfl_sync(0xffffffffu, t, 0); // (tells the compiler the step counter is warp-uniform: no divergence bookkeeping)
             const bool go = ((rowpar + t) & 1) ? step(I0{}, I1{}) : step(I0{}, I0{});
             if (!go) break;
             // position k of the next step = position k-1 of this one; with ROT = 0 position k is entry (RR - k) % RR
@@ -656,6 +663,9 @@ __device__ __forceinline__ void tma_pass_piece(const GridP& g, const PassMaps& m
         if (lane == 0 && wm > 0.f) atomicMax(wmax, __float_as_uint(wm));
     }
 }
+#undef pou
+#undef pow_
+#undef pov
 
 template <int K, int NW, bool FORCE, bool MAXW>
 __global__ void __launch_bounds__(NW * 32, 1)

@@ -9,6 +9,7 @@
 #include <nvtx3/nvToolsExt.h> // header-only (NVTX v3): ranges per stage for Nsight Systems timelines
 
 #include <algorithm>
+#include <array>
 #include <climits>
 #include <cmath>
 #include <cstdint>
@@ -180,6 +181,7 @@ struct smk_sim {
         int nboundary[2];
     };
     std::vector<DevSchedule> schedules;
+    std::vector<std::array<int, 5>> zchunk_cache; // pick_zchunk_tma: {tx, ty, K, planes, chunk}
     std::vector<const void*> configured; // kernels whose dynamic shared-memory limit has been raised on this handle's device
     std::string err;
 };
@@ -411,6 +413,41 @@ int pick_zchunk(const smk_sim* s, int tiles_xy, int K, int nzn)
     return (nzn + best_n - 1) / best_n;
 }
 
+// ... for the TMA-staged pass (one CTA per SM; pieces of the bottom tile row -- the floor, COMPLEX cells -- run the
+// compact general variant, ~1.45x per z-step, and are handed out first): list-schedule every candidate chunk count on
+// the SMs the way the hardware dispatches the grid (next CTA to the first SM that frees up) and keep the shortest span.
+int pick_zchunk_tma(smk_sim* s, int tx, int ty, int K, int nzn)
+{
+    for (const auto& e : s->zchunk_cache) // (the search costs milliseconds of host time: once per shape, not per launch)
+        if (e[0] == tx && e[1] == ty && e[2] == K && e[3] == nzn) return e[4];
+    const int sms = std::max(1, s->num_sms);
+    int best_n = 1;
+    double best = 1e300;
+    std::vector<double> busy;
+    for (int n = 1; n <= std::max(1, nzn / (2 * K)); n++) {
+        const int zc = (nzn + n - 1) / n;
+        const int nch = (nzn + zc - 1) / zc;
+        if (nch != n) continue;
+        busy.assign((size_t)sms, 0.0);
+        auto put = [&](double cost) { // (a heap would do; the lists are a few hundred entries)
+            auto it = std::min_element(busy.begin(), busy.end());
+            *it += cost;
+        };
+        const double setup = 1.5; // prologue + pipeline fill of a piece, in z-steps
+        for (int pass = 0; pass < 2; pass++)
+            for (int c = 0; c < nch; c++) {
+                const int planes = std::min(zc, nzn - c * zc);
+                const double steps = planes + 2 * K + setup;
+                if (pass == 0) for (int i = 0; i < tx; i++) put(1.45 * steps);
+                else for (int i = 0; i < tx * (ty - 1); i++) put(steps);
+            }
+        const double span = *std::max_element(busy.begin(), busy.end());
+        if (span < best - 1e-9) { best = span; best_n = n; }
+    }
+    s->zchunk_cache.push_back({tx, ty, K, nzn, (nzn + best_n - 1) / best_n});
+    return s->zchunk_cache.back()[4];
+}
+
 int ensure_scratch(smk_sim*) { return SMK_OK; } // the scratch set is part of the arena
 
 // cudaFuncSetAttribute applies to the CURRENT device only: remembered per handle, not per process
@@ -578,7 +615,7 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
     // (kernels_pressure_tma.cuh, the default wherever its tensor maps exist)
     static const char* kenv = getenv("SMK_PASS_KERNEL");
     static const bool use_lean = kenv && strcmp(kenv, "lean") == 0;
-    bool use_tma = NW == 16 && s->pass_tma_ok && kenv && strcmp(kenv, "tma") == 0; // (work in progress: opt-in until it beats reg)
+    bool use_tma = NW == 16 && s->pass_tma_ok && !use_lean && !(kenv && strcmp(kenv, "reg") == 0); // the default where its tensor maps exist
     if (use_tma && s->pending_force && !s->pass_tma_smoke_ok) use_tma = false;
     if (use_tma && from_peers && ((s->peer[0].arena && !s->pass_tma_peer_ok[0]) || (s->peer[1].arena && !s->pass_tma_peer_ok[1]))) use_tma = false;
     {
@@ -638,7 +675,7 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
                                plane0(s->w[s->now], g.nplane, g.zlo), g.zlo, plane0(s->smoke[s->now], g.cplane, g.zlo)};
     const int nz = out_hi - out_lo;
     const int tx = (g.W + 1 + C::OX - 1) / C::OX, ty = (g.SY + C::OY - 1) / C::OY;
-    int zchunk = pick_zchunk(s, tx * ty, K, nz);
+    int zchunk = use_tma ? pick_zchunk_tma(s, tx, ty, K, nz) : pick_zchunk(s, tx * ty, K, nz);
     static const int force_chunks = getenv("SMK_PASS_NCHUNKS") ? atoi(getenv("SMK_PASS_NCHUNKS")) : 0; // experiments
     if (force_chunks > 0) zchunk = std::max(K, (nz + force_chunks - 1) / force_chunks);
     // the lean kernel addresses a chunk with 32-bit byte offsets: (planes of a chunk incl. lead-in) x plane bytes < 2^32

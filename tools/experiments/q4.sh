@@ -1,0 +1,6 @@
+export SMK_PASS_KERNEL=tma
+D=smoke-simulation_b200
+q() { python bench.py --workload $1 --steps 10 --warmup 3 --no-cpu-baseline --no-extras --no-verify 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); r=d['roofline']; print('$1 $2', round(d['ms_per_step'],3), round(r['launch_ms'],4), round(r['frac_compulsory'],3))"; }
+for v in nopipe pipe nopipe pipe; do cp $D/variant_$v.so.bin $D/libsmoke_b200.so; q C2 $v; q C3 $v; done
+cp $D/variant_nopipe.so.bin $D/libsmoke_b200.so
+SMK_PASS_DEBUG=1 timeout 60 python tools/cta_times.py C2 20 2>&1 | grep -E "lean|general|busy"
