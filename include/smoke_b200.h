@@ -129,6 +129,12 @@ float* smk_buoyancy_ptr(smk_sim* s);
  * fuse = number of half-sweeps fused per kernel launch (temporal blocking); 0 = library default,
  * 1 = one launch per half-sweep.  Results are identical for every fuse value. */
 int smk_set_solver(smk_sim* s, int variant, int iterations, int fuse);
+/* Which kernel runs the fused red-black passes (same bits either way; tests run both):
+ *   SMK_PASS_AUTO  TMA-staged kernel (kernels_pressure_tma.cuh) on grids of >= 5 M nodes per slab, the round-1 kernel
+ *                  (kernels_pressure_reg.cuh) below -- small grids are launch-bound and its prologue is shorter;
+ *   SMK_PASS_REG / SMK_PASS_TMA  force one.  Process-wide default: SMK_PASS_KERNEL=reg|tma in the environment. */
+enum { SMK_PASS_AUTO = 0, SMK_PASS_REG = 1, SMK_PASS_TMA = 2 };
+int smk_set_pass_kernel(smk_sim* s, int kind);
 /* scheduling of the fused pressure passes (no effect on results): 0 = default, a (tile, z-chunk) grid of CTAs;
  * nctas > 0 = that many CTAs working through balanced piece lists (csrc/pass_schedule.h; an experiment kept for
  * ablation: measured no faster). */

@@ -27,6 +27,10 @@ _vp = C.c_void_p
 _i = C.c_int
 
 
+PASS_KERNELS = {"auto": 0, "reg": 1, "tma": 2}
+DEFAULT_PASS_KERNEL = None   # tests set this to run every case with each pass kernel (SmokeSim.__init__ applies it)
+
+
 class SmokeError(RuntimeError):
     pass
 
@@ -75,6 +79,7 @@ def load_library():
     L.smk_buoyancy_ptr.argtypes = [_vp]
     L.smk_buoyancy_ptr.restype = C.POINTER(_f)
     L.smk_set_solver.argtypes = [_vp, _i, _i, _i]
+    L.smk_set_pass_kernel.argtypes = [_vp, _i]
     L.smk_set_pass_ctas.argtypes = [_vp, _i]
     L.smk_set_readback_box.argtypes = [_vp, _i]
     L.smk_last_pass_ctas.argtypes = [_vp]
@@ -173,6 +178,8 @@ class SmokeSim:
         if rc != 0:
             raise SmokeError(f"smk_create failed ({rc}): {self.L.smk_last_error(None).decode()}")
         self._cb = None
+        if DEFAULT_PASS_KERNEL is not None:
+            self.set_pass_kernel(DEFAULT_PASS_KERNEL)
 
     # -- lifetime
     def close(self):
@@ -226,6 +233,7 @@ class SmokeSim:
 
     def set_obstacle_mode(self, union_mode): self._ck(self.L.smk_set_obstacle_mode(self.h, int(union_mode)))
 
+    def set_pass_kernel(self, kind): self._ck(self.L.smk_set_pass_kernel(self.h, PASS_KERNELS.get(kind, kind)))
     def set_solver(self, variant=0, iterations=30, fuse=0): self._ck(self.L.smk_set_solver(self.h, variant, iterations, fuse))
     def set_pass_ctas(self, nctas): self._ck(self.L.smk_set_pass_ctas(self.h, int(nctas)))
     def last_pass_ctas(self): return int(self.L.smk_last_pass_ctas(self.h))

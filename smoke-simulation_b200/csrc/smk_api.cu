@@ -141,6 +141,7 @@ struct smk_sim {
     CUtensorMap pmap_code;
     CUtensorMap pmap_smoke[3][2];
     bool pass_tma_ok = false, pass_tma_smoke_ok = false;
+    int pass_kernel = SMK_PASS_AUTO; // smk_set_pass_kernel
     bool pass_tma_peer_ok[2] = {false, false};
 
     // host ranges this handle page-locked for the density readback (smk_register_host, or implicitly by smk_step)
@@ -615,7 +616,13 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
     // (kernels_pressure_tma.cuh, the default wherever its tensor maps exist)
     static const char* kenv = getenv("SMK_PASS_KERNEL");
     static const bool use_lean = kenv && strcmp(kenv, "lean") == 0;
-    bool use_tma = NW == 16 && s->pass_tma_ok && !use_lean && !(kenv && strcmp(kenv, "reg") == 0); // the default where its tensor maps exist
+    // per handle (smk_set_pass_kernel), else the process default from the environment, else automatic
+    const int kind = s->pass_kernel != SMK_PASS_AUTO ? s->pass_kernel
+                     : (kenv && strcmp(kenv, "reg") == 0) ? SMK_PASS_REG : (kenv && strcmp(kenv, "tma") == 0) ? SMK_PASS_TMA : SMK_PASS_AUTO;
+    bool use_tma = NW == 16 && s->pass_tma_ok && !use_lean && kind != SMK_PASS_REG; // the default where its tensor maps exist
+    // small grids are launch- and pipeline-fill-bound, and there the round-1 kernel's shorter prologue wins (measured
+    // crossover between 160^3 and 192^3: profiles/r2_tma_pass_final.txt); smk_set_pass_kernel / SMK_PASS_KERNEL=tma force it anyway
+    if (use_tma && kind != SMK_PASS_TMA && (long long)g.P * g.SY * (out_hi - out_lo) < 5000000ll) use_tma = false;
     if (use_tma && s->pending_force && !s->pass_tma_smoke_ok) use_tma = false;
     if (use_tma && from_peers && ((s->peer[0].arena && !s->pass_tma_peer_ok[0]) || (s->peer[1].arena && !s->pass_tma_peer_ok[1]))) use_tma = false;
     {
@@ -1770,6 +1777,13 @@ int smk_set_obstacle_mode(smk_sim* s, int mode)
 
 float* smk_gravity_ptr(smk_sim* s) { return s ? &s->gravity : nullptr; }
 float* smk_buoyancy_ptr(smk_sim* s) { return s ? &s->alpha : nullptr; }
+
+int smk_set_pass_kernel(smk_sim* s, int kind)
+{
+    if (!s || kind < SMK_PASS_AUTO || kind > SMK_PASS_TMA) return SMK_ERR_ARG;
+    s->pass_kernel = kind;
+    return SMK_OK;
+}
 
 int smk_set_solver(smk_sim* s, int variant, int iterations, int fuse)
 {

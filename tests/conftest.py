@@ -30,6 +30,25 @@ def smk():
     return m
 
 
+def pytest_generate_tests(metafunc):
+    """Every GPU test runs twice: the fused pressure passes on the TMA-staged kernel and on the round-1 kernel (the
+    automatic choice depends on the grid size, and the test grids are small).  CPU tests run once."""
+    if metafunc.definition.get_closest_marker("gpu") is not None and "pass_kernel" in metafunc.fixturenames:
+        metafunc.parametrize("pass_kernel", ["tma", "reg"], indirect=True)
+
+
+@pytest.fixture(autouse=True)
+def pass_kernel(request):
+    kind = getattr(request, "param", None)
+    if kind is None:
+        yield None
+        return
+    from smoke_simulation_b200 import binding
+    binding.DEFAULT_PASS_KERNEL = kind
+    yield kind
+    binding.DEFAULT_PASS_KERNEL = None
+
+
 def rel_err(a, b):
     """max|a-b| / max|b| -- the parity metric of SURVEY.md section 8(c)."""
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)

@@ -23,12 +23,13 @@ def _ngpu():
 @pytest.mark.parametrize("transport,dims,mode", [("p2p", (64, 48, 40), "plain"), ("p2p", (70, 33, 24), "plain"), ("nccl", (64, 48, 40), "plain"),
                                                  ("p2p", (256, 256, 80), "plain"), ("p2p", (96, 64, 48), "hitch"), ("nccl", (96, 64, 48), "hitch"),
                                                  ("p2p", (96, 64, 48), "reach")])
-def test_slabs_across_processes_bit_identical(transport, dims, mode):
+def test_slabs_across_processes_bit_identical(transport, dims, mode, pass_kernel):
     n = _ngpu()
     if n < 2:
         pytest.skip("needs at least two GPUs")
     world = 4 if n >= 4 else 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "tools", "mp_check.py"), transport] + [str(v) for v in dims] + [mode]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    env = dict(os.environ, SMK_PASS_KERNEL=pass_kernel)   # the ranks are separate processes: the process-wide switch
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0 and ("OK (bit-identical" in r.stdout or "OK (SMK_ERR_REACH" in r.stdout), r.stdout[-2000:] + r.stderr[-2000:]
