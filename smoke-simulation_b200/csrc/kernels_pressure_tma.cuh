@@ -684,12 +684,18 @@ k_pressure_tma(GridP g, const __grid_constant__ PassMaps maps, float* __restrict
 
     // CTAs are dispatched in linear block order and a piece of the bottom tile row (the floor: COMPLEX cells, the
     // slower variant) takes ~1.5x as long as the others: hand those out first, so that they never form the tail.
+    // With the in-kernel handshake (PassSync) the boundary chunks sit at the end of the z order unless this is the
+    // first pass of a step (they wait for the neighbours, so they start as late as possible): their floor pieces stay
+    // with them -- interior floor, interior rest, boundary floor, boundary rest.
     int bx = (int)blockIdx.x, by = (int)blockIdx.y, bz = (int)blockIdx.z;
-    if (pr.sync.nchunks == 0 && gridDim.y > 1) {
+    if (gridDim.y > 1) {
         const int gx = (int)gridDim.x, gy = (int)gridDim.y, gz = (int)gridDim.z;
-        int L = bx + gx * (by + gy * bz);
-        if (L < gx * gz) { by = 0; bx = L % gx; bz = L / gx; }
-        else { L -= gx * gz; bx = L % gx; L /= gx; by = 1 + L % (gy - 1); bz = L / (gy - 1); }
+        const int zb = (pr.sync.nchunks > 0 && !pr.sync.first) ? min(gz, 2) : 0; // trailing boundary z's
+        const int za = gz - zb;
+        int L = bx + gx * (by + gy * bz), z0 = 0, nz = za;
+        if (L >= gx * gy * za) { L -= gx * gy * za; z0 = za; nz = zb; }
+        if (L < gx * nz) { by = 0; bx = L % gx; bz = z0 + L / gx; }
+        else { L -= gx * nz; bx = L % gx; L /= gx; by = 1 + L % (gy - 1); bz = z0 + L / (gy - 1); }
     }
     int chunk = pr.chunk_first + bz * pr.chunk_step;
     int bside = -1; // this CTA reads / serves the neighbour on that side (PassSync, kernels_pressure_reg.cuh)

@@ -45,33 +45,56 @@ def main():
     if mode == "hitch":
         dts[2] = 0.5          # u, v, w ~ U(-4, 4) after projection: backtraces of 2-3 planes (the reference passes wall-clock dt)
     if mode == "reach":
-        dts[1] = 16.0         # the clamp bounds the reach by 3 sqrt(dt) = 12 planes: beyond ghost - 1 -> every slab rank must raise SMK_ERR_REACH, not return stale data
-    reach_err = 0
-    for t in range(steps):
-        try:
-            sim.step(dts[t], host)
-        except smk.SmokeError as ex:
-            if mode == "reach" and "error 4" in str(ex):
-                reach_err = 1
-                break
-            raise
-        ref.step(dts[t], ref_host)
-    if mode == "reach":
-        tot = torch.tensor([reach_err], device="cuda"); dist.all_reduce(tot, op=dist.ReduceOp.MIN)
-        if rank == 0:
-            print(f"mp_check {transport} world={world} grid={W}x{H}x{D} reach: " + ("OK (SMK_ERR_REACH raised on every rank)" if int(tot.item()) else "FAILED (no SMK_ERR_REACH)"), flush=True)
-        sim.close(); ref.close(); dist.barrier(); dist.destroy_process_group()
-        sys.exit(0 if int(tot.item()) else 1)
+        dts[1] = 16.0         # the clamp bounds the reach by 3 sqrt(dt) = 12 planes: beyond ghost - 1 -> the slabs whose backtraces leave their valid planes raise SMK_ERR_REACH, nobody returns stale data
     g = smk.slab.geometry(W, H, D, world, rank, ghost)
-    bad = []
-    for f, name in ((po.U, "u"), (po.V, "v"), (po.W, "w")):
+
+    def mismatches():
+        bad = []
+        for f, name in ((po.U, "u"), (po.V, "v"), (po.W, "w")):
+            for which in (po.NOW, po.PAST):
+                sl = slice(g["own_node_lo"], g["own_node_hi"] + 1)
+                if not np.array_equal(sim.get_field(f, which)[sl], ref.get_field(f, which)[sl]):
+                    bad.append((name, which))
         for which in (po.NOW, po.PAST):
-            sl = slice(g["own_node_lo"], g["own_node_hi"] + 1)
-            if not np.array_equal(sim.get_field(f, which)[sl], ref.get_field(f, which)[sl]):
-                bad.append((name, which))
-    for which in (po.NOW, po.PAST):
-        if not np.array_equal(sim.get_field(po.SMOKE, which)[g["c0"]:g["c1"]], ref.get_field(po.SMOKE, which)[g["c0"]:g["c1"]]):
-            bad.append(("smoke", which))
+            if not np.array_equal(sim.get_field(po.SMOKE, which)[g["c0"]:g["c1"]], ref.get_field(po.SMOKE, which)[g["c0"]:g["c1"]]):
+                bad.append(("smoke", which))
+        return bad
+
+    if mode == "reach":
+        # SMK_ERR_REACH is per rank: a slab raises it when ITS backtraces left its valid planes.  The ranks agree on stopping
+        # after every step (what an application's driver has to do: a rank that carried on would wait for neighbours that
+        # stopped); a rank that did NOT raise must hold exactly the single-GPU result of that step -- never stale data.
+        raised_on, stale = [], 0
+        for t in range(steps):
+            mine = 0
+            try:
+                sim.step(dts[t], host)
+            except smk.SmokeError as ex:
+                if "error 4" not in str(ex):
+                    print(f"mp_check rank {rank}: step {t} failed: {ex}", flush=True)
+                    raise
+                mine = 1
+            ref.step(dts[t], ref_host)
+            flags = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(world)]
+            dist.all_gather(flags, torch.tensor([mine], dtype=torch.int32, device="cuda"))
+            raised_on = [r for r in range(world) if int(flags[r].item())]
+            if raised_on:
+                if not mine and mismatches():
+                    stale = 1
+                    print(f"mp_check rank {rank}: no SMK_ERR_REACH but the slab differs from the single-GPU run: {mismatches()}", flush=True)
+                break
+        tot = torch.tensor([stale], device="cuda"); dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        ok = bool(raised_on) and not int(tot.item())
+        if rank == 0:
+            print(f"mp_check {transport} world={world} grid={W}x{H}x{D} reach: " +
+                  (f"OK (SMK_ERR_REACH raised on ranks {raised_on}; every other rank identical to the single-GPU run)" if ok
+                   else "FAILED (no SMK_ERR_REACH)" if not raised_on else "FAILED (stale data without SMK_ERR_REACH)"), flush=True)
+        sim.close(); ref.close(); dist.barrier(); dist.destroy_process_group()
+        sys.exit(0 if ok else 1)
+    for t in range(steps):
+        sim.step(dts[t], host)
+        ref.step(dts[t], ref_host)
+    bad = mismatches()
     if not np.array_equal(host[g["c0"]:g["c1"]], ref_host[g["c0"]:g["c1"]]):
         bad.append(("host readback", 0))
     ok = torch.tensor([0 if bad else 1], device="cuda")
