@@ -39,14 +39,15 @@ UNIT = "voxel-steps/s"
 BYTES_PER_CELL_HALFSWEEP = 25  # u,v,w read+write (24 B) + 1 B mask information per cell
 
 
-def ncu_traffic(wname, hs_per_launch):
+def ncu_traffic(wname, hs_per_launch, kname="reg"):
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the committed
     `ncu --set full` captures: profiles/ncu_traffic.json maps "<workload>:<half-sweeps per launch>" to
     {"bytes": ..., "source": "profiles/<capture summary>"}.  None when no capture of that configuration is committed."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             t = json.load(f)
-        return t.get(f"{wname}:{int(round(hs_per_launch))}")
+        key = f"{wname}:{int(round(hs_per_launch))}"
+        return t.get(f"{key}:{kname}") if kname != "reg" else t.get(key)
     except Exception:
         return None
 
@@ -270,7 +271,7 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def pressure_roofline(times, K, sweeps, cells_local, wname, world, peak, peak_src, jac, bal):
+def pressure_roofline(times, K, sweeps, cells_local, wname, world, peak, peak_src, jac, bal, kname="reg"):
     """Roofline object of the dominant kernel (the pressure pass) from the library's own CUDA-event stage timers."""
     p_ms, p_launches = times["pressure"]
     per_launch_ms = p_ms / max(p_launches, 1)
@@ -278,13 +279,15 @@ def pressure_roofline(times, K, sweeps, cells_local, wname, world, peak, peak_sr
     compulsory_bytes = BYTES_PER_CELL_HALFSWEEP * cells_local   # u,v,w read + written once, 1 B of mask information
     alg_bytes = compulsory_bytes * hs_per_launch                # section 8(d): 25 B per cell and HALF-SWEEP x half-sweeps per launch
     achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
-    tr = ncu_traffic(wname, hs_per_launch) if world == 1 else None
+    tr = ncu_traffic(wname, hs_per_launch, kname) if world == 1 else None
     return {
         "bound": "hbm",
         "kernel": ((f"k_jacobi_bal ({bal} CTAs, balanced piece lists)" if bal else "k_jacobi") +
                    ": one damped-Jacobi iteration per launch (extension)" if jac else
                    (f"balanced piece lists on {bal} CTAs, " if bal else "") +
-                   "fused pressure pass: 4 red/black SOR half-sweeps per launch (temporal blocking, register-resident u,w)"
+                   ("k_pressure_tma<4,16> (TMA-staged planes, kernels_pressure_tma.cuh)" if kname == "tma" else
+                    "k_pressure_reg<4,16> (kernels_pressure_reg.cuh)") +
+                   ": fused pressure pass, 4 red/black SOR half-sweeps per launch (temporal blocking, register-resident u,w)"
                    if hs_per_launch > 1.5 else "k_pressure_half: one red/black SOR half-sweep per launch"),
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": tr["bytes"] if tr else None, "traffic_source": tr["source"] if tr else None,
@@ -552,7 +555,7 @@ def main():
         cells = W * H * D
         cells_local = W * H * (c1 - c0)                      # one launch of the dominant kernel covers one slab
         bal = sim.last_pass_ctas()
-        roofline = pressure_roofline(times, K, sweeps, cells_local, wname, world, peak, peak_src, jac, bal)
+        roofline = pressure_roofline(times, K, sweeps, cells_local, wname, world, peak, peak_src, jac, bal, sim.last_pass_kernel())
         cfg = workload_config(label, scene, args.solver, iters, world, explicit)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
@@ -581,12 +584,13 @@ def main():
                 sc3 = po.SCENES["C3"]
                 k3 = max(3, K // 4)
                 ms3, ms3e, t3, s3 = time_single_gpu(smk, po, torch, sc3, stream, k3, 2, True, iters, False, args.fuse)
+                k3name = s3.last_pass_kernel()
                 s3.close()
                 n3 = sc3[0] * sc3[1] * sc3[2]
                 line["c3_512"] = {"workload": "C3 512^3 plume with solid-sphere obstacle; reference schedule RBGS omega=1.9 x30",
                                   "value": n3 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3, "steps": k3, "warmup": 2,
                                   "e2e": {"value": n3 / (ms3e * 1e-3), "ms_per_step": ms3e, "d2h_bytes_per_step": n3 * 4},
-                                  "roofline": pressure_roofline(t3, k3, sweeps, n3, "C3", 1, peak, peak_src, False, 0)}
+                                  "roofline": pressure_roofline(t3, k3, sweeps, n3, "C3", 1, peak, peak_src, False, 0, k3name)}
             except Exception as ex:   # pragma: no cover
                 line["c3_512"] = {"unavailable": str(ex)}
         if not args.no_cpu_baseline and world == 1:

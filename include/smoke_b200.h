@@ -135,6 +135,8 @@ int smk_set_solver(smk_sim* s, int variant, int iterations, int fuse);
  *   SMK_PASS_REG / SMK_PASS_TMA  force one.  Process-wide default: SMK_PASS_KERNEL=reg|tma in the environment. */
 enum { SMK_PASS_AUTO = 0, SMK_PASS_REG = 1, SMK_PASS_TMA = 2 };
 int smk_set_pass_kernel(smk_sim* s, int kind);
+/* SMK_PASS_REG / SMK_PASS_TMA: the kernel the most recent fused pass ran on (0: none yet) -- bench.py names it */
+int smk_last_pass_kernel(smk_sim* s);
 /* scheduling of the fused pressure passes (no effect on results): 0 = default, a (tile, z-chunk) grid of CTAs;
  * nctas > 0 = that many CTAs working through balanced piece lists (csrc/pass_schedule.h; an experiment kept for
  * ablation: measured no faster). */

@@ -80,6 +80,7 @@ def load_library():
     L.smk_buoyancy_ptr.restype = C.POINTER(_f)
     L.smk_set_solver.argtypes = [_vp, _i, _i, _i]
     L.smk_set_pass_kernel.argtypes = [_vp, _i]
+    L.smk_last_pass_kernel.argtypes = [_vp]
     L.smk_set_pass_ctas.argtypes = [_vp, _i]
     L.smk_set_readback_box.argtypes = [_vp, _i]
     L.smk_last_pass_ctas.argtypes = [_vp]
@@ -234,6 +235,7 @@ class SmokeSim:
     def set_obstacle_mode(self, union_mode): self._ck(self.L.smk_set_obstacle_mode(self.h, int(union_mode)))
 
     def set_pass_kernel(self, kind): self._ck(self.L.smk_set_pass_kernel(self.h, PASS_KERNELS.get(kind, kind)))
+    def last_pass_kernel(self): return {1: "reg", 2: "tma"}.get(int(self.L.smk_last_pass_kernel(self.h)), "none")
     def set_solver(self, variant=0, iterations=30, fuse=0): self._ck(self.L.smk_set_solver(self.h, variant, iterations, fuse))
     def set_pass_ctas(self, nctas): self._ck(self.L.smk_set_pass_ctas(self.h, int(nctas)))
     def last_pass_ctas(self): return int(self.L.smk_last_pass_ctas(self.h))

@@ -105,6 +105,7 @@ struct smk_sim {
     int fuse = 0;
     int pass_ctas = getenv("SMK_PASS_CTAS") ? atoi(getenv("SMK_PASS_CTAS")) : 0; // smk_set_pass_ctas (0: chunk grid)
     int last_pass_ctas = 0; // CTAs of the last balanced pass launch (0: it was a (tile, z-chunk) grid)
+    int last_pass_kernel = 0; // SMK_PASS_REG / SMK_PASS_TMA: what the last fused pass ran on
 
     // slab decomposition (single GPU: owns everything, no ghosts); schedule and validity tracking in slab_plan.h
     slab::Geom geom{};
@@ -662,9 +663,11 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
                     k<<<grid, T0::THREADS, T0::SMEM_END, st>>>(g, m, s->scratch[0], s->scratch[1], s->scratch[2], sweep0, zchunk_, r, fa, s->d_dyn, s->d_flags, cf, s->d_passdbg);
                 }
                 s->passdbg_ctas = (int)(grid.x * grid.y * grid.z);
+                s->last_pass_kernel = SMK_PASS_TMA;
                 return;
             }
         }
+        s->last_pass_kernel = SMK_PASS_REG;
         if (use_lean) {
             auto k = force ? (maxw ? smk::k_pressure_lean<K, NW, true, true> : smk::k_pressure_lean<K, NW, true, false>)
                            : (maxw ? smk::k_pressure_lean<K, NW, false, true> : smk::k_pressure_lean<K, NW, false, false>);
@@ -1803,6 +1806,7 @@ int smk_set_pass_ctas(smk_sim* s, int nctas)
 }
 
 int smk_last_pass_ctas(smk_sim* s) { return s ? s->last_pass_ctas : -SMK_ERR_ARG; }
+int smk_last_pass_kernel(smk_sim* s) { return s ? s->last_pass_kernel : -SMK_ERR_ARG; }
 
 int smk_set_readback_box(smk_sim* s, int on)
 {
