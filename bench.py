@@ -502,6 +502,24 @@ def main():
                                "api": "smk_step_async(sim, dt, host_density): device snapshot + D2H on a second stream, "
                                       "overlapped with the next step; wall clock around K steps + smk_sync"}
 
+        # ---- extra (one GPU): sparse blocking readback (smk_set_readback_box): only the rows that can hold smoke are
+        # copied, the caller's buffer ends up identical to the full copy as long as the caller does not write to it
+        if world == 1:
+            sim.set_readback_box(1)
+            for _ in range(2):
+                sim.step_ptr(po.tick_dt(tick), host_ptr); tick += 1   # the first call copies everything
+            rbs = sim.readback_bytes()
+            w0 = time.perf_counter()
+            for _ in range(K):
+                sim.step_ptr(po.tick_dt(tick), host_ptr); tick += 1
+            ms_sp = (time.perf_counter() - w0) * 1e3
+            extras["sparse_readback"] = {"value": W * H * D * K / (ms_sp * 1e-3), "ms_per_step": ms_sp / K,
+                                         "d2h_bytes_per_step": (sim.readback_bytes() - rbs) / K,
+                                         "api": "smk_set_readback_box(sim, 1) + smk_step(sim, dt, host_density): blocking, same buffer "
+                                                "contents as the full copy (tests/test_parity_gaps_gpu.py), opt-in because the caller "
+                                                "must not write to the buffer between steps"}
+            sim.set_readback_box(0)
+
     # ---- N > 1: bit-identity with the single-GPU run of the SAME domain, at the bench size --------------------
     # Every rank hashes its owned planes on the device (smk_hash_owned); rank 0 then steps the whole domain on its own
     # GPU for the same ticks and hashes the same plane ranges (smk_hash_range).
