@@ -395,7 +395,7 @@ __device__ __forceinline__ void tma_issue_plane(const IssueArgs& q, int z, int s
 }
 
 // One PIECE of a pass: the tile (bx, by) marched over the output node planes [zo0, zo1) (K lead-in planes below, K - 1
-// above).  MAXW: also reduce max |w| over the planes written (bound of the next advection's backtrace in z).
+// above).
 //
 // Step t:  (a) write out v of plane t-K-1;  (b) ENTER plane t+1 -- wait for its staged copy, registers + v ring;
 //          (c) K sweeps on planes t-1 .. t-K;  (d) write out u, w of plane t-K;  (e) barrier.
@@ -405,11 +405,11 @@ __device__ __forceinline__ void tma_issue_plane(const IssueArgs& q, int z, int s
 // The register ring has K+2 entries; plane p lives in entry (p - t0 + c) mod (K+2) for its whole life, and the loop is
 // unrolled over the K+2 rotations (no ring shift; round 1 moved 36 registers per step).  K+2 is even, so the rotation
 // also fixes the x parity of the active colour (c = parity of the warp's first step selects where it enters the pattern).
-template <int K, int NW, bool FORCE, bool MAXW, bool GENERAL>
+template <int K, int NW, bool FORCE, bool GENERAL>
 __device__ __forceinline__ void tma_pass_piece(const GridP& g, const PassMaps& maps, float* __restrict__ uo, float* __restrict__ vo,
                                                float* __restrict__ wo, int sweep0, const PassRange& pr, const ForceArgs& fa,
                                                unsigned char* __restrict__ smem, int bx, int by, int zo0, int zo1,
-                                               unsigned* __restrict__ wmax, int* __restrict__ flags, long long* __restrict__ trace = nullptr)
+                                               int* __restrict__ flags, long long* __restrict__ trace = nullptr)
 {
     using C = TmaCfg<K, NW, FORCE>;
     constexpr int LY = C::LY, RR = K + 2, NS = C::NS;
@@ -484,7 +484,6 @@ __device__ __forceinline__ void tma_pass_piece(const GridP& g, const PassMaps& m
 #define pou (uo + oo)
 #define pow_ (wo + oo)
 #define pov (vo + (oo - g.nplane))
-    float wm = 0.f;
 
     unsigned tt = 0;            // (t - t0) << 13: slot bits of plane t in the v ring (masked)
     int ss = 0;                 // staging slot of plane t+1 (the plane that enters during step t)
@@ -598,7 +597,6 @@ __device__ __forceinline__ void tma_pass_piece(const GridP& g, const PassMaps& m
                 const b64 ue = UE[ph_of(K)], uq = UO[ph_of(K)], we = WE[ph_of(K)], wq = WO[ph_of(K)];
                 *reinterpret_cast<float4*>(pou) = make_float4(lo32(ue), lo32(uq), hi32(ue), hi32(uq));
                 *reinterpret_cast<float4*>(pow_) = make_float4(lo32(we), lo32(wq), hi32(we), hi32(wq));
-                if (MAXW) wm = fmaxf(fmaxf(fmaxf(wm, fabsf(lo32(we))), fmaxf(fabsf(lo32(wq)), fabsf(hi32(we)))), fabsf(hi32(wq)));
             }
             oo += g.nplane;
         }
@@ -658,19 +656,15 @@ __device__ __forceinline__ void tma_pass_piece(const GridP& g, const PassMaps& m
         }
     }
     if (failed) return;
-    if (MAXW) {
-        for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
-        if (lane == 0 && wm > 0.f) atomicMax(wmax, __float_as_uint(wm));
-    }
 }
 #undef pou
 #undef pow_
 #undef pov
 
-template <int K, int NW, bool FORCE, bool MAXW>
+template <int K, int NW, bool FORCE>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_pressure_tma(GridP g, const __grid_constant__ PassMaps maps, float* __restrict__ uo, float* __restrict__ vo, float* __restrict__ wo,
-               int sweep0, int zchunk, PassRange pr, ForceArgs fa, unsigned* __restrict__ wmax, int* __restrict__ flags,
+               int sweep0, int zchunk, PassRange pr, ForceArgs fa, int* __restrict__ flags,
                const unsigned char* __restrict__ cflag, long long* __restrict__ dbg)
 {
     const long long dbg_t0 = dbg ? clock64() : 0;
@@ -733,9 +727,9 @@ k_pressure_tma(GridP g, const __grid_constant__ PassMaps maps, float* __restrict
             for (int z = za + (int)threadIdx.x; z <= zb; z += (int)blockDim.x) cx |= cflag[(long long)(z - g.zlo) * per + me];
             cx = __syncthreads_or(cx);
         }
-        if (cx) tma_pass_piece<K, NW, FORCE, MAXW, true>(g, maps, uo, vo, wo, sweep0, pr, fa, smem_raw, bx, by, zo0, zo1, wmax, flags,
+        if (cx) tma_pass_piece<K, NW, FORCE, true>(g, maps, uo, vo, wo, sweep0, pr, fa, smem_raw, bx, by, zo0, zo1, flags,
                                                          (dbg && bx == dbg[(1 << 17) - 3] && by == dbg[(1 << 17) - 2] && bz == dbg[(1 << 17) - 1]) ? dbg + (1 << 17) : nullptr);
-        else tma_pass_piece<K, NW, FORCE, MAXW, false>(g, maps, uo, vo, wo, sweep0, pr, fa, smem_raw, bx, by, zo0, zo1, wmax, flags,
+        else tma_pass_piece<K, NW, FORCE, false>(g, maps, uo, vo, wo, sweep0, pr, fa, smem_raw, bx, by, zo0, zo1, flags,
                                                        (dbg && bx == dbg[(1 << 17) - 3] && by == dbg[(1 << 17) - 2] && bz == dbg[(1 << 17) - 1]) ? dbg + (1 << 17) : nullptr);
         if (dbg && threadIdx.x == 0) { // development aid (SMK_PASS_DEBUG): per-CTA start, duration, SM and variant
             unsigned smid;

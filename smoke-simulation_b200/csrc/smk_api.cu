@@ -24,7 +24,6 @@
 #include "kernels_basic.cuh"
 #include "kernels_pressure_fused.cuh"
 #include "kernels_pressure_reg.cuh"
-#include "kernels_pressure_lean.cuh"
 #include "kernels_pressure_tma.cuh"
 #include "kernels_advect_tma.cuh"
 #include "kernels_jacobi.cuh"
@@ -92,7 +91,6 @@ struct smk_sim {
 
     int solver = SMK_SOLVER_RBGS;
     int pass_epoch_next = -1;   // half-sweep index whose handshake epoch the previous pass kernel publishes itself
-    bool want_maxw = false;     // the next fused pass also reduces max |w| over the planes it writes into d_dyn[0]
     long long* d_passdbg = nullptr; // SMK_PASS_DEBUG=1: {start clock, cycles, SM id, variant} of every CTA of the last fused pass
     int passdbg_ctas = 0;
     unsigned* d_dyn = nullptr;  // device words: [0] max |w| bits (atomicMax), [1] advection margin in planes
@@ -612,15 +610,13 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
 {
     using C = smk::RegCfg<K, NW>;
     const GridP& g = s->g;
-    // SMK_PASS_KERNEL=reg | lean | tma selects the pass kernel for same-box A/B runs: the round-1 kernel
-    // (kernels_pressure_reg.cuh), its LDG-based rewrite (kernels_pressure_lean.cuh) or the TMA-staged kernel
-    // (kernels_pressure_tma.cuh, the default wherever its tensor maps exist)
+    // SMK_PASS_KERNEL=reg | tma: process-wide choice of the pass kernel for same-box A/B runs -- the round-1 kernel
+    // (kernels_pressure_reg.cuh) or the TMA-staged kernel (kernels_pressure_tma.cuh)
     static const char* kenv = getenv("SMK_PASS_KERNEL");
-    static const bool use_lean = kenv && strcmp(kenv, "lean") == 0;
     // per handle (smk_set_pass_kernel), else the process default from the environment, else automatic
     const int kind = s->pass_kernel != SMK_PASS_AUTO ? s->pass_kernel
                      : (kenv && strcmp(kenv, "reg") == 0) ? SMK_PASS_REG : (kenv && strcmp(kenv, "tma") == 0) ? SMK_PASS_TMA : SMK_PASS_AUTO;
-    bool use_tma = NW == 16 && s->pass_tma_ok && !use_lean && kind != SMK_PASS_REG; // the default where its tensor maps exist
+    bool use_tma = NW == 16 && s->pass_tma_ok && kind != SMK_PASS_REG; // the default where its tensor maps exist
     // small grids are launch- and pipeline-fill-bound, and there the round-1 kernel's shorter prologue wins (measured
     // crossover between 160^3 and 192^3: profiles/r2_tma_pass_final.txt); smk_set_pass_kernel / SMK_PASS_KERNEL=tma force it anyway
     if (use_tma && kind != SMK_PASS_TMA && (long long)g.P * g.SY * (out_hi - out_lo) < 5000000ll) use_tma = false;
@@ -629,16 +625,12 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
     {
         int rc0;
         if ((rc0 = ensure_smem(s, smk::k_pressure_reg<K, NW, false>, C::SMEM)) || (rc0 = ensure_smem(s, smk::k_pressure_reg<K, NW, true>, C::SMEM)) ||
-            (rc0 = ensure_smem(s, smk::k_pressure_reg_bal<K, NW, false>, C::SMEM)) || (rc0 = ensure_smem(s, smk::k_pressure_reg_bal<K, NW, true>, C::SMEM)) ||
-            (rc0 = ensure_smem(s, smk::k_pressure_lean<K, NW, false, false>, C::SMEM)) || (rc0 = ensure_smem(s, smk::k_pressure_lean<K, NW, true, false>, C::SMEM)) ||
-            (rc0 = ensure_smem(s, smk::k_pressure_lean<K, NW, false, true>, C::SMEM)) || (rc0 = ensure_smem(s, smk::k_pressure_lean<K, NW, true, true>, C::SMEM)))
+            (rc0 = ensure_smem(s, smk::k_pressure_reg_bal<K, NW, false>, C::SMEM)) || (rc0 = ensure_smem(s, smk::k_pressure_reg_bal<K, NW, true>, C::SMEM)))
             return rc0;
     }
     // forcing + clamp deferred to this pass (exec_op / stage_pressure): the first pass of the step applies them on load
     const bool force = s->pending_force;
     s->pending_force = false;
-    const bool maxw = s->want_maxw; // the last pass of a slab step also reduces max |w| (adaptive advection margin)
-    s->want_maxw = false;
     const smk::ForceArgs fa{s->smoke[s->now], s->pending_dt, s->gravity, s->alpha};
     const int n = s->now;
     auto launch_k = [&](dim3 grid, cudaStream_t st, int zchunk_, const smk::PassRange& r) {
@@ -654,13 +646,13 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
                 using T0 = smk::TmaCfg<K, 16, false>;
                 using T1 = smk::TmaCfg<K, 16, true>;
                 if (force) {
-                    auto k = maxw ? smk::k_pressure_tma<K, 16, true, true> : smk::k_pressure_tma<K, 16, true, false>;
+                    auto k = smk::k_pressure_tma<K, 16, true>;
                     if (ensure_smem(s, k, T1::SMEM_END)) return;
-                    k<<<grid, T1::THREADS, T1::SMEM_END, st>>>(g, m, s->scratch[0], s->scratch[1], s->scratch[2], sweep0, zchunk_, r, fa, s->d_dyn, s->d_flags, cf, s->d_passdbg);
+                    k<<<grid, T1::THREADS, T1::SMEM_END, st>>>(g, m, s->scratch[0], s->scratch[1], s->scratch[2], sweep0, zchunk_, r, fa, s->d_flags, cf, s->d_passdbg);
                 } else {
-                    auto k = maxw ? smk::k_pressure_tma<K, 16, false, true> : smk::k_pressure_tma<K, 16, false, false>;
+                    auto k = smk::k_pressure_tma<K, 16, false>;
                     if (ensure_smem(s, k, T0::SMEM_END)) return;
-                    k<<<grid, T0::THREADS, T0::SMEM_END, st>>>(g, m, s->scratch[0], s->scratch[1], s->scratch[2], sweep0, zchunk_, r, fa, s->d_dyn, s->d_flags, cf, s->d_passdbg);
+                    k<<<grid, T0::THREADS, T0::SMEM_END, st>>>(g, m, s->scratch[0], s->scratch[1], s->scratch[2], sweep0, zchunk_, r, fa, s->d_flags, cf, s->d_passdbg);
                 }
                 s->passdbg_ctas = (int)(grid.x * grid.y * grid.z);
                 s->last_pass_kernel = SMK_PASS_TMA;
@@ -668,14 +660,8 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
             }
         }
         s->last_pass_kernel = SMK_PASS_REG;
-        if (use_lean) {
-            auto k = force ? (maxw ? smk::k_pressure_lean<K, NW, true, true> : smk::k_pressure_lean<K, NW, true, false>)
-                           : (maxw ? smk::k_pressure_lean<K, NW, false, true> : smk::k_pressure_lean<K, NW, false, false>);
-            k<<<grid, C::THREADS, C::SMEM, st>>>(g, s->scratch[0], s->scratch[1], s->scratch[2], s->pcode, sweep0, zchunk_, r, fa, s->d_dyn);
-        } else {
-            auto k = force ? smk::k_pressure_reg<K, NW, true> : smk::k_pressure_reg<K, NW, false>;
-            k<<<grid, C::THREADS, C::SMEM, st>>>(g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk_, r, fa);
-        }
+        auto k = force ? smk::k_pressure_reg<K, NW, true> : smk::k_pressure_reg<K, NW, false>;
+        k<<<grid, C::THREADS, C::SMEM, st>>>(g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, zchunk_, r, fa);
     };
     smk::PassRange pr{};
     pr.out_lo = out_lo; pr.out_hi = out_hi;
@@ -688,7 +674,7 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
     int zchunk = use_tma ? pick_zchunk_tma(s, tx, ty, K, nz) : pick_zchunk(s, tx * ty, K, nz);
     static const int force_chunks = getenv("SMK_PASS_NCHUNKS") ? atoi(getenv("SMK_PASS_NCHUNKS")) : 0; // experiments
     if (force_chunks > 0) zchunk = std::max(K, (nz + force_chunks - 1) / force_chunks);
-    // the lean kernel addresses a chunk with 32-bit byte offsets: (planes of a chunk incl. lead-in) x plane bytes < 2^32
+    // (kept from a precursor kernel that addressed a chunk with 32-bit byte offsets; harmless: it only splits huge chunks)
     while ((long long)(zchunk + 2 * K + 2) * g.nplane * 4 >= (1ll << 32) && zchunk > 2 * K) zchunk = (zchunk + 1) / 2;
     // Only the first and the last z-chunk may touch planes within K of the slab ends (the neighbours read those / they
     // read the neighbours'): the LAST chunk must therefore hold at least K planes too (the others hold zchunk >= K)
