@@ -56,39 +56,42 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
                  ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
-// staged planes of one field: tile-local coordinates, ring slot from the global plane index
-struct Staged {
-    const float* base; // [NSLOT][SLOT_FLOATS]
+// The staged window of one z-step, shared by the three fields (they are staged with the same box): planes
+// z-HALO .. z+HALO in ring slots sb, sb+1, ... (mod NSLOT), box origin (x0, y0).
+struct Window {
     int x0, y0;        // global coordinates of box element (0,0)
-    int zc;            // plane being computed: planes zc-HALO .. zc+HALO are resident
-    int sb;            // ring slot of plane zc-HALO
-    __device__ __forceinline__ bool holds(int xa, int xb, int ya, int yb, int za, int zb) const
-    {
-        return xa >= x0 && xb < x0 + AdvTma::BX && ya >= y0 && yb < y0 + AdvTma::BY && za >= zc - AdvTma::HALO && zb <= zc + AdvTma::HALO;
-    }
-    __device__ __forceinline__ const float* row(int y, int z) const
-    {
-        int slot = sb + (z - zc + AdvTma::HALO);   // z in [zc-HALO, zc+HALO] (holds()): one conditional wrap, no modulo
-        slot -= slot >= AdvTma::NSLOT ? AdvTma::NSLOT : 0;
-        return base + slot * AdvTma::SLOT_FLOATS + (y - y0) * AdvTma::BX - x0;
-    }
-    __device__ __forceinline__ float at(int x, int y, int z) const { return row(y, z)[x]; }
+    int zlo, zhi;      // planes a sample may read: the staged ones that also hold valid data (reach guard of slab runs)
+    int zbase;         // plane in slot sb (= z - HALO)
+    int sb;            // ring slot of that plane
 };
 
 // clamped trilinear sample (sampleSmoke cu:451-484): same index / weight / summation code as sample_global, the
-// eight corners come from the staged planes when they are all resident
-__device__ __forceinline__ float sample_staged(const Staged& s, const float* __restrict__ f, long long sy, long long sz, int zlo,
-                                               float px, float py, float pz, float dx, float dy, float dz,
-                                               float bx, float by, float bz, int2 zv, int* __restrict__ flag)
+// eight corners come from the staged planes when they are all resident.  fs = the field's staging ring.
+// Addressing: i1 - i0 is 0 or 1 on every axis (tri_axis), so one unsigned compare per axis covers both corners, the
+// second row / plane / column is the first plus a selected stride, and nothing is multiplied twice.
+__device__ __forceinline__ float sample_staged(const Window& w, const float* __restrict__ fs, const float* __restrict__ f,
+                                               long long sy, long long sz, int zlo, float px, float py, float pz,
+                                               float dx, float dy, float dz, float bx, float by, float bz, int2 zv,
+                                               int* __restrict__ flag)
 {
+    using A = AdvTma;
     Tri t;
     tri_axis(px, dx, bx, t.x0, t.x1, t.xw0, t.xw1);
     tri_axis(py, dy, by, t.y0, t.y1, t.yw0, t.yw1);
     tri_axis(pz, dz, bz, t.z0, t.z1, t.zw0, t.zw1);
-    if (s.holds(t.x0, t.x1, t.y0, t.y1, t.z0, t.z1) && t.z0 >= zv.x && t.z1 <= zv.y) {
-        const float* r00 = s.row(t.y0, t.z0); const float* r10 = s.row(t.y1, t.z0);
-        const float* r01 = s.row(t.y0, t.z1); const float* r11 = s.row(t.y1, t.z1);
-        return tri_combine(t, r00[t.x0], r00[t.x1], r10[t.x0], r10[t.x1], r01[t.x0], r01[t.x1], r11[t.x0], r11[t.x1]);
+    const unsigned rx = (unsigned)(t.x0 - w.x0), ry = (unsigned)(t.y0 - w.y0);
+    // (a corner pair that is clamped onto the last staged column / row / plane takes the global path: domain edges only)
+    if (rx < (unsigned)(A::BX - 1) && ry < (unsigned)(A::BY - 1) && t.z0 >= w.zlo && t.z0 < w.zhi) {
+        int s0 = w.sb + (t.z0 - w.zbase);
+        s0 -= s0 >= A::NSLOT ? A::NSLOT : 0;
+        const float* r00 = fs + s0 * A::SLOT_FLOATS + (int)ry * A::BX + (int)rx;
+        const int oy = t.y1 != t.y0 ? A::BX : 0;
+        const int oz = t.z1 != t.z0 ? (s0 == A::NSLOT - 1 ? -(A::NSLOT - 1) * A::SLOT_FLOATS : A::SLOT_FLOATS) : 0;
+        const int ox = t.x1 - t.x0;
+        const float* r10 = r00 + oy;
+        const float* r01 = r00 + oz;
+        const float* r11 = r01 + oy;
+        return tri_combine(t, r00[0], r00[ox], r10[0], r10[ox], r01[0], r01[ox], r11[0], r11[ox]);
     }
     return sample_global(f, sy, sz, zlo, px, py, pz, dx, dy, dz, bx, by, bz, zv, flag); // long backtrace: global path
 }
@@ -137,6 +140,9 @@ k_advect_velocity_tma(GridP g, const __grid_constant__ CUtensorMap mu, const __g
     const long long P = g.P, S = g.nplane;
     const bool xy_ok = x >= 1 && y >= 1 && x < g.W && y < g.H;
 
+    // this node inside a staged plane, and the ring slot of plane z - HALO (both advance without a division)
+    const int o = (y - by0) * A::BX + (x - bx0);
+    int sb = (z_first - A::HALO + 4 * A::NSLOT) % A::NSLOT;
     for (int z = z_first; z < z_last; z++) {
         // every plane p is waited for exactly once, when it enters the window as z+HALO (the first step waits for all five)
         for (int p = (z == z_first ? z - A::HALO : z + A::HALO); p <= z + A::HALO; p++) {
@@ -150,53 +156,62 @@ k_advect_velocity_tma(GridP g, const __grid_constant__ CUtensorMap mu, const __g
             const bool doV = (cd & CODE_SELF) && (cd & CODE_SY0) && x < g.W - 1 && z < g.D - 1;
             const bool doW = (cd & CODE_SELF) && (cd & CODE_SZ0) && x < g.W - 1 && y < g.H - 1;
             if (doU || doV || doW) {
-                const int sb = (z - A::HALO + 4 * A::NSLOT) % A::NSLOT;
-                const Staged U{su, bx0, by0, z, sb}, V{sv, bx0, by0, z, sb}, Wf{sw, bx0, by0, z, sb};
+                // planes z-1 and z of the three fields at this node: every neighbour below is base + immediate
+                int s1 = sb + A::HALO - 1, s2 = sb + A::HALO;
+                s1 -= s1 >= A::NSLOT ? A::NSLOT : 0;
+                s2 -= s2 >= A::NSLOT ? A::NSLOT : 0;
+                const int om = s1 * A::SLOT_FLOATS + o, o0 = s2 * A::SLOT_FLOATS + o;
+                const float* Um = su + om; const float* U0 = su + o0;
+                const float* Vm = sv + om; const float* V0 = sv + o0;
+                const float* Wm = sw + om; const float* W0 = sw + o0;
+                constexpr int BX = A::BX;
+                const Window win{bx0, by0, max(z - A::HALO, zv.x), min(z + A::HALO, zv.y), z - A::HALO, sb};
                 const long long n = node_index(g, x, y, z);
                 // 8-point face sums in the reference's order (avgU/avgV/avgW cu:409-447), then *0.125
                 float au = 0.f, av = 0.f, aw = 0.f;
                 if (doV || doW) {
-                    float a = U.at(x, y, z - 1);
-                    a = __fadd_rn(a, U.at(x + 1, y, z - 1)); a = __fadd_rn(a, U.at(x, y - 1, z - 1)); a = __fadd_rn(a, U.at(x + 1, y - 1, z - 1));
-                    a = __fadd_rn(a, U.at(x, y, z)); a = __fadd_rn(a, U.at(x + 1, y, z)); a = __fadd_rn(a, U.at(x, y - 1, z));
-                    a = __fadd_rn(a, U.at(x + 1, y - 1, z));
+                    float a = Um[0];
+                    a = __fadd_rn(a, Um[1]); a = __fadd_rn(a, Um[-BX]); a = __fadd_rn(a, Um[1 - BX]);
+                    a = __fadd_rn(a, U0[0]); a = __fadd_rn(a, U0[1]); a = __fadd_rn(a, U0[-BX]);
+                    a = __fadd_rn(a, U0[1 - BX]);
                     au = __fmul_rn(a, 0.125f);
                 }
                 if (doU || doW) {
-                    float a = V.at(x, y, z - 1);
-                    a = __fadd_rn(a, V.at(x - 1, y, z - 1)); a = __fadd_rn(a, V.at(x, y + 1, z - 1)); a = __fadd_rn(a, V.at(x - 1, y + 1, z - 1));
-                    a = __fadd_rn(a, V.at(x, y, z)); a = __fadd_rn(a, V.at(x - 1, y, z)); a = __fadd_rn(a, V.at(x, y + 1, z));
-                    a = __fadd_rn(a, V.at(x - 1, y + 1, z));
+                    float a = Vm[0];
+                    a = __fadd_rn(a, Vm[-1]); a = __fadd_rn(a, Vm[BX]); a = __fadd_rn(a, Vm[BX - 1]);
+                    a = __fadd_rn(a, V0[0]); a = __fadd_rn(a, V0[-1]); a = __fadd_rn(a, V0[BX]);
+                    a = __fadd_rn(a, V0[BX - 1]);
                     av = __fmul_rn(a, 0.125f);
                 }
                 if (doU || doV) {
-                    float a = Wf.at(x, y, z);
-                    a = __fadd_rn(a, Wf.at(x - 1, y, z)); a = __fadd_rn(a, Wf.at(x, y - 1, z)); a = __fadd_rn(a, Wf.at(x - 1, y - 1, z));
-                    a = __fadd_rn(a, Wf.at(x, y, z - 1)); a = __fadd_rn(a, Wf.at(x - 1, y, z - 1)); a = __fadd_rn(a, Wf.at(x, y - 1, z - 1));
-                    a = __fadd_rn(a, Wf.at(x - 1, y - 1, z - 1));
+                    float a = W0[0];
+                    a = __fadd_rn(a, W0[-1]); a = __fadd_rn(a, W0[-BX]); a = __fadd_rn(a, W0[-BX - 1]);
+                    a = __fadd_rn(a, Wm[0]); a = __fadd_rn(a, Wm[-1]); a = __fadd_rn(a, Wm[-BX]);
+                    a = __fadd_rn(a, Wm[-BX - 1]);
                     aw = __fmul_rn(a, 0.125f);
                 }
                 const float xh = half_up(x), yh = half_up(y), zh = half_up(z);
                 if (doU) {
-                    const float px = __fmaf_rn(-U.at(x, y, z), dt, (float)x);
+                    const float px = __fmaf_rn(-U0[0], dt, (float)x);
                     const float py = __fmaf_rn(-av, dt, yh);
                     const float pz = __fmaf_rn(-aw, dt, zh);
-                    u1[n] = sample_staged(U, u0, P, S, g.zlo, px, py, pz, 0.f, .5f, .5f, bx, by, bz, zv, flag);
+                    u1[n] = sample_staged(win, su, u0, P, S, g.zlo, px, py, pz, 0.f, .5f, .5f, bx, by, bz, zv, flag);
                 }
                 if (doV) {
                     const float px = __fmaf_rn(-au, dt, xh);
-                    const float py = __fmaf_rn(-V.at(x, y, z), dt, (float)y);
+                    const float py = __fmaf_rn(-V0[0], dt, (float)y);
                     const float pz = __fmaf_rn(-aw, dt, zh);
-                    v1[n] = sample_staged(V, v0, P, S, g.zlo, px, py, pz, .5f, 0.f, .5f, bx, by, bz, zv, flag);
+                    v1[n] = sample_staged(win, sv, v0, P, S, g.zlo, px, py, pz, .5f, 0.f, .5f, bx, by, bz, zv, flag);
                 }
                 if (doW) {
                     const float px = __fmaf_rn(-au, dt, xh);
                     const float py = __fmaf_rn(-av, dt, yh);
-                    const float pz = __fmaf_rn(-Wf.at(x, y, z), dt, (float)z);
-                    w1[n] = sample_staged(Wf, w0, P, S, g.zlo, px, py, pz, .5f, .5f, 0.f, bx, by, bz, zv, flag);
+                    const float pz = __fmaf_rn(-W0[0], dt, (float)z);
+                    w1[n] = sample_staged(win, sw, w0, P, S, g.zlo, px, py, pz, .5f, .5f, 0.f, bx, by, bz, zv, flag);
                 }
             }
         }
+        sb = sb + 1 == A::NSLOT ? 0 : sb + 1;
         __syncthreads(); // plane z-HALO is no longer read: its slot may take plane z+HALO+1
         if (tid == 0 && z + 1 < z_last) issue(z + A::HALO + 1);
     }
