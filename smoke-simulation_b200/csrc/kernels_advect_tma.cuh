@@ -84,14 +84,16 @@ __device__ __forceinline__ float sample_staged(const Window& w, const float* __r
     if (rx < (unsigned)(A::BX - 1) && ry < (unsigned)(A::BY - 1) && t.z0 >= w.zlo && t.z0 < w.zhi) {
         int s0 = w.sb + (t.z0 - w.zbase);
         s0 -= s0 >= A::NSLOT ? A::NSLOT : 0;
-        const float* r00 = fs + s0 * A::SLOT_FLOATS + (int)ry * A::BX + (int)rx;
-        const int oy = t.y1 != t.y0 ? A::BX : 0;
-        const int oz = t.z1 != t.z0 ? (s0 == A::NSLOT - 1 ? -(A::NSLOT - 1) * A::SLOT_FLOATS : A::SLOT_FLOATS) : 0;
-        const int ox = t.x1 - t.x0;
-        const float* r10 = r00 + oy;
-        const float* r01 = r00 + oz;
-        const float* r11 = r01 + oy;
-        return tri_combine(t, r00[0], r00[ox], r10[0], r10[ox], r01[0], r01[ox], r11[0], r11[ox]);
+        // byte offsets from here on: the second row / plane / column of the eight corners is one add each
+        const char* r00 = reinterpret_cast<const char*>(fs + s0 * A::SLOT_FLOATS + (int)ry * A::BX + (int)rx);
+        const int oy = t.y1 != t.y0 ? A::BX * 4 : 0;
+        const int oz = t.z1 != t.z0 ? (s0 == A::NSLOT - 1 ? -(A::NSLOT - 1) * A::SLOT_BYTES : A::SLOT_BYTES) : 0;
+        const int ox = (t.x1 - t.x0) * 4;
+        const char* r10 = r00 + oy;
+        const char* r01 = r00 + oz;
+        const char* r11 = r01 + oy;
+        auto ld = [](const char* q) { return *reinterpret_cast<const float*>(q); };
+        return tri_combine(t, ld(r00), ld(r00 + ox), ld(r10), ld(r10 + ox), ld(r01), ld(r01 + ox), ld(r11), ld(r11 + ox));
     }
     return sample_global(f, sy, sz, zlo, px, py, pz, dx, dy, dz, bx, by, bz, zv, flag); // long backtrace: global path
 }
@@ -143,15 +145,19 @@ k_advect_velocity_tma(GridP g, const __grid_constant__ CUtensorMap mu, const __g
     // this node inside a staged plane, and the ring slot of plane z - HALO (both advance without a division)
     const int o = (y - by0) * A::BX + (x - bx0);
     int sb = (z_first - A::HALO + 4 * A::NSLOT) % A::NSLOT;
+    // the stencil code of the node is the one global load in front of everything else of a z-step: fetched a step ahead
+    auto load_code = [&](int z) -> unsigned { return (xy_ok && z >= 1 && z < g.D) ? code[code_index(g, x, y, z)] : 0u; };
+    unsigned cd_next = load_code(z_first);
     for (int z = z_first; z < z_last; z++) {
+        const unsigned cd = cd_next;
+        if (z + 1 < z_last) cd_next = load_code(z + 1);
         // every plane p is waited for exactly once, when it enters the window as z+HALO (the first step waits for all five)
         for (int p = (z == z_first ? z - A::HALO : z + A::HALO); p <= z + A::HALO; p++) {
             const int slot = (p + 4 * A::NSLOT) % A::NSLOT;
             const unsigned use = (unsigned)((p - (z_first - A::HALO)) / A::NSLOT); // how often the slot was filled before
             if (!mbar_wait(&bars[slot], use & 1u)) { flag[2] = 1; return; }
         }
-        if (xy_ok && z >= 1 && z < g.D) {
-            const unsigned cd = code[code_index(g, x, y, z)];
+        if (cd & CODE_SELF) { // (0 outside the node range)
             const bool doU = (cd & CODE_SELF) && (cd & CODE_SX0) && y < g.H - 1 && z < g.D - 1;
             const bool doV = (cd & CODE_SELF) && (cd & CODE_SY0) && x < g.W - 1 && z < g.D - 1;
             const bool doW = (cd & CODE_SELF) && (cd & CODE_SZ0) && x < g.W - 1 && y < g.H - 1;
