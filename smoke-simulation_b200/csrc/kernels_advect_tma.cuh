@@ -42,10 +42,13 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
 // bounded wait: returns false after ~2^26 polls instead of hanging the GPU on a lost transaction
 __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned parity)
 {
+#pragma unroll 1
     for (int it = 0; it < (1 << 26); it++) {
         unsigned ok;
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        // (suspend-time hint: a thread that finds the plane still in flight sleeps until the barrier flips instead of
+        //  polling -- the profile showed 14 probes per thread and z-step, 6 % of the kernel's issue slots)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
         if (ok) return true;
     }
     return false;
