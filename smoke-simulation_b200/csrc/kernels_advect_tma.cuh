@@ -59,6 +59,16 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
                  ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
+// One 32-bit shared-memory load at lane address + immediate.  The kernel addresses its staging rings with explicit
+// shared-window addresses: through generic pointers the compiler rebuilt the window base (S2R / LEA) at every use.
+template <int OFF>
+__device__ __forceinline__ float lds32(unsigned a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF) : "memory");
+    return v;
+}
+
 // The staged window of one z-step, shared by the three fields (they are staged with the same box): planes
 // z-HALO .. z+HALO in ring slots sb, sb+1, ... (mod NSLOT), box origin (x0, y0).
 struct Window {
@@ -69,10 +79,10 @@ struct Window {
 };
 
 // clamped trilinear sample (sampleSmoke cu:451-484): same index / weight / summation code as sample_global, the
-// eight corners come from the staged planes when they are all resident.  fs = the field's staging ring.
-// Addressing: i1 - i0 is 0 or 1 on every axis (tri_axis), so one unsigned compare per axis covers both corners, the
-// second row / plane / column is the first plus a selected stride, and nothing is multiplied twice.
-__device__ __forceinline__ float sample_staged(const Window& w, const float* __restrict__ fs, const float* __restrict__ f,
+// eight corners come from the staged planes when they are all resident.  fs = shared-window address of the field's
+// staging ring.  Addressing: i1 - i0 is 0 or 1 on every axis (tri_axis), so one unsigned compare per axis covers both
+// corners, the second row / plane / column is the first plus a selected stride, and nothing is multiplied twice.
+__device__ __forceinline__ float sample_staged(const Window& w, unsigned fs, const float* __restrict__ f,
                                                long long sy, long long sz, int zlo, float px, float py, float pz,
                                                float dx, float dy, float dz, float bx, float by, float bz, int2 zv,
                                                int* __restrict__ flag)
@@ -87,16 +97,13 @@ __device__ __forceinline__ float sample_staged(const Window& w, const float* __r
     if (rx < (unsigned)(A::BX - 1) && ry < (unsigned)(A::BY - 1) && t.z0 >= w.zlo && t.z0 < w.zhi) {
         int s0 = w.sb + (t.z0 - w.zbase);
         s0 -= s0 >= A::NSLOT ? A::NSLOT : 0;
-        // byte offsets from here on: the second row / plane / column of the eight corners is one add each
-        const char* r00 = reinterpret_cast<const char*>(fs + s0 * A::SLOT_FLOATS + (int)ry * A::BX + (int)rx);
-        const int oy = t.y1 != t.y0 ? A::BX * 4 : 0;
-        const int oz = t.z1 != t.z0 ? (s0 == A::NSLOT - 1 ? -(A::NSLOT - 1) * A::SLOT_BYTES : A::SLOT_BYTES) : 0;
-        const int ox = (t.x1 - t.x0) * 4;
-        const char* r10 = r00 + oy;
-        const char* r01 = r00 + oz;
-        const char* r11 = r01 + oy;
-        auto ld = [](const char* q) { return *reinterpret_cast<const float*>(q); };
-        return tri_combine(t, ld(r00), ld(r00 + ox), ld(r10), ld(r10 + ox), ld(r01), ld(r01 + ox), ld(r11), ld(r11 + ox));
+        const unsigned r00 = fs + (unsigned)(s0 * A::SLOT_FLOATS + (int)ry * A::BX + (int)rx) * 4u;
+        const unsigned oy = t.y1 != t.y0 ? A::BX * 4 : 0;
+        const unsigned oz = t.z1 != t.z0 ? (s0 == A::NSLOT - 1 ? (unsigned)(-(A::NSLOT - 1) * A::SLOT_BYTES) : (unsigned)A::SLOT_BYTES) : 0u;
+        const unsigned ox = (unsigned)(t.x1 - t.x0) * 4u;
+        const unsigned r10 = r00 + oy, r01 = r00 + oz, r11 = r01 + oy;
+        return tri_combine(t, lds32<0>(r00), lds32<0>(r00 + ox), lds32<0>(r10), lds32<0>(r10 + ox),
+                           lds32<0>(r01), lds32<0>(r01 + ox), lds32<0>(r11), lds32<0>(r11 + ox));
     }
     return sample_global(f, sy, sz, zlo, px, py, pz, dx, dy, dz, bx, by, bz, zv, flag); // long backtrace: global path
 }
@@ -115,6 +122,7 @@ k_advect_velocity_tma(GridP g, const __grid_constant__ CUtensorMap mu, const __g
     float* sv = su + A::NSLOT * A::SLOT_FLOATS;
     float* sw = sv + A::NSLOT * A::SLOT_FLOATS;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sw + A::NSLOT * A::SLOT_FLOATS);
+    const unsigned su_a = smem_u32(su), sv_a = smem_u32(sv), sw_a = smem_u32(sw);
 
     const int tid = threadIdx.x;
     const int lx = tid % A::TX, ly = tid / A::TX;
@@ -130,99 +138,109 @@ k_advect_velocity_tma(GridP g, const __grid_constant__ CUtensorMap mu, const __g
     }
     __syncthreads();
 
-    // plane p (global index) -> slot; tensor-map z coordinate is relative to the first stored plane
-    auto issue = [&](int p) {
-        const int slot = (p + 4 * A::NSLOT) % A::NSLOT;
+    // Planes are numbered from the first one this piece stages, i = p - (z_first - HALO), and live in slot i mod NSLOT:
+    // slot and barrier parity advance by counting, without a division per step.
+    const int p0 = z_first - A::HALO;
+    auto issue = [&](int p, int slot) {
         mbar_expect_tx(&bars[slot], 3u * A::PLANE * 4u);
         tma_load_3d(su + slot * A::SLOT_FLOATS, &mu, bx0, by0, p - g.zlo, &bars[slot]);
         tma_load_3d(sv + slot * A::SLOT_FLOATS, &mv, bx0, by0, p - g.zlo, &bars[slot]);
         tma_load_3d(sw + slot * A::SLOT_FLOATS, &mw, bx0, by0, p - g.zlo, &bars[slot]);
     };
     if (tid == 0)
-        for (int p = z_first - A::HALO; p <= z_first + A::HALO; p++) issue(p);
+        for (int i = 0; i <= 2 * A::HALO; i++) issue(p0 + i, i);
 
     const float bx = (float)(unsigned)(g.W - 1), by = (float)(unsigned)(g.H - 1), bz = (float)(unsigned)(g.D - 1);
     const long long P = g.P, S = g.nplane;
     const bool xy_ok = x >= 1 && y >= 1 && x < g.W && y < g.H;
-
-    // this node inside a staged plane, and the ring slot of plane z - HALO (both advance without a division)
-    const int o = (y - by0) * A::BX + (x - bx0);
-    int sb = (z_first - A::HALO + 4 * A::NSLOT) % A::NSLOT;
+    // per-thread constants of the z march: which components this column can ever write, the node's corner (x-1, y-1)
+    // inside a staged plane (every neighbour of the face sums is that address + a non-negative immediate), running
+    // offsets of the node and of its stencil code
+    const unsigned needU = (xy_ok && y < g.H - 1) ? (unsigned)(CODE_SELF | CODE_SX0) : 0x100u; // 0x100: never matches a byte
+    const unsigned needV = (xy_ok && x < g.W - 1) ? (unsigned)(CODE_SELF | CODE_SY0) : 0x100u;
+    const unsigned needW = (xy_ok && x < g.W - 1 && y < g.H - 1) ? (unsigned)(CODE_SELF | CODE_SZ0) : 0x100u;
+    const unsigned corner = (unsigned)((y - by0 - 1) * A::BX + (x - bx0 - 1)) * 4u;
+    const float xf = (float)x, yf = (float)y, xh = half_up(x), yh = half_up(y);
+    long long n = xy_ok ? node_index(g, x, y, z_first) : 0;
+    const unsigned char* pc = code + (xy_ok ? code_index(g, x, y, z_first) : 0);
+    constexpr int BX4 = A::BX * 4;
+    constexpr int C00 = BX4 + 4;                  // the node itself, relative to its corner
+    auto load_code = [&](int z) -> unsigned { return (xy_ok && z >= 1 && z < g.D) ? (unsigned)*pc : 0u; };
     // the stencil code of the node is the one global load in front of everything else of a z-step: fetched a step ahead
-    auto load_code = [&](int z) -> unsigned { return (xy_ok && z >= 1 && z < g.D) ? code[code_index(g, x, y, z)] : 0u; };
     unsigned cd_next = load_code(z_first);
+    int sb = 0;                                   // slot of plane z - HALO
+    int ws = 2 * A::HALO;                         // slot of plane z + HALO, the one a step waits for ...
+    unsigned wpar = 0;                            // ... and the parity of its barrier
     for (int z = z_first; z < z_last; z++) {
         const unsigned cd = cd_next;
+        pc += g.kplane;
         if (z + 1 < z_last) cd_next = load_code(z + 1);
-        // every plane p is waited for exactly once, when it enters the window as z+HALO (the first step waits for all five)
-        for (int p = (z == z_first ? z - A::HALO : z + A::HALO); p <= z + A::HALO; p++) {
-            const int slot = (p + 4 * A::NSLOT) % A::NSLOT;
-            const unsigned use = (unsigned)((p - (z_first - A::HALO)) / A::NSLOT); // how often the slot was filled before
-            if (!mbar_wait(&bars[slot], use & 1u)) { flag[2] = 1; return; }
+        // every plane is waited for exactly once, when it enters the window as z+HALO (the first step waits for all five)
+        if (z == z_first) {
+            for (int i = 0; i < 2 * A::HALO; i++)
+                if (!mbar_wait(&bars[i], 0u)) { flag[2] = 1; return; }
         }
-        if (cd & CODE_SELF) { // (0 outside the node range)
-            const bool doU = (cd & CODE_SELF) && (cd & CODE_SX0) && y < g.H - 1 && z < g.D - 1;
-            const bool doV = (cd & CODE_SELF) && (cd & CODE_SY0) && x < g.W - 1 && z < g.D - 1;
-            const bool doW = (cd & CODE_SELF) && (cd & CODE_SZ0) && x < g.W - 1 && y < g.H - 1;
-            if (doU || doV || doW) {
-                // planes z-1 and z of the three fields at this node: every neighbour below is base + immediate
-                int s1 = sb + A::HALO - 1, s2 = sb + A::HALO;
-                s1 -= s1 >= A::NSLOT ? A::NSLOT : 0;
-                s2 -= s2 >= A::NSLOT ? A::NSLOT : 0;
-                const int om = s1 * A::SLOT_FLOATS + o, o0 = s2 * A::SLOT_FLOATS + o;
-                const float* Um = su + om; const float* U0 = su + o0;
-                const float* Vm = sv + om; const float* V0 = sv + o0;
-                const float* Wm = sw + om; const float* W0 = sw + o0;
-                constexpr int BX = A::BX;
-                const Window win{bx0, by0, max(z - A::HALO, zv.x), min(z + A::HALO, zv.y), z - A::HALO, sb};
-                const long long n = node_index(g, x, y, z);
-                // 8-point face sums in the reference's order (avgU/avgV/avgW cu:409-447), then *0.125
-                float au = 0.f, av = 0.f, aw = 0.f;
-                if (doV || doW) {
-                    float a = Um[0];
-                    a = __fadd_rn(a, Um[1]); a = __fadd_rn(a, Um[-BX]); a = __fadd_rn(a, Um[1 - BX]);
-                    a = __fadd_rn(a, U0[0]); a = __fadd_rn(a, U0[1]); a = __fadd_rn(a, U0[-BX]);
-                    a = __fadd_rn(a, U0[1 - BX]);
-                    au = __fmul_rn(a, 0.125f);
-                }
-                if (doU || doW) {
-                    float a = Vm[0];
-                    a = __fadd_rn(a, Vm[-1]); a = __fadd_rn(a, Vm[BX]); a = __fadd_rn(a, Vm[BX - 1]);
-                    a = __fadd_rn(a, V0[0]); a = __fadd_rn(a, V0[-1]); a = __fadd_rn(a, V0[BX]);
-                    a = __fadd_rn(a, V0[BX - 1]);
-                    av = __fmul_rn(a, 0.125f);
-                }
-                if (doU || doV) {
-                    float a = W0[0];
-                    a = __fadd_rn(a, W0[-1]); a = __fadd_rn(a, W0[-BX]); a = __fadd_rn(a, W0[-BX - 1]);
-                    a = __fadd_rn(a, Wm[0]); a = __fadd_rn(a, Wm[-1]); a = __fadd_rn(a, Wm[-BX]);
-                    a = __fadd_rn(a, Wm[-BX - 1]);
-                    aw = __fmul_rn(a, 0.125f);
-                }
-                const float xh = half_up(x), yh = half_up(y), zh = half_up(z);
-                if (doU) {
-                    const float px = __fmaf_rn(-U0[0], dt, (float)x);
-                    const float py = __fmaf_rn(-av, dt, yh);
-                    const float pz = __fmaf_rn(-aw, dt, zh);
-                    u1[n] = sample_staged(win, su, u0, P, S, g.zlo, px, py, pz, 0.f, .5f, .5f, bx, by, bz, zv, flag);
-                }
-                if (doV) {
-                    const float px = __fmaf_rn(-au, dt, xh);
-                    const float py = __fmaf_rn(-V0[0], dt, (float)y);
-                    const float pz = __fmaf_rn(-aw, dt, zh);
-                    v1[n] = sample_staged(win, sv, v0, P, S, g.zlo, px, py, pz, .5f, 0.f, .5f, bx, by, bz, zv, flag);
-                }
-                if (doW) {
-                    const float px = __fmaf_rn(-au, dt, xh);
-                    const float py = __fmaf_rn(-av, dt, yh);
-                    const float pz = __fmaf_rn(-W0[0], dt, (float)z);
-                    w1[n] = sample_staged(win, sw, w0, P, S, g.zlo, px, py, pz, .5f, .5f, 0.f, bx, by, bz, zv, flag);
-                }
+        if (!mbar_wait(&bars[ws], wpar)) { flag[2] = 1; return; }
+        const bool zin = z < g.D - 1;
+        const bool doU = (cd & needU) == needU && zin;
+        const bool doV = (cd & needV) == needV && zin;
+        const bool doW = (cd & needW) == needW;
+        if (doU || doV || doW) {
+            // planes z-1 and z of the three fields at this node's corner
+            int s1 = sb + A::HALO - 1, s2 = sb + A::HALO;
+            s1 -= s1 >= A::NSLOT ? A::NSLOT : 0;
+            s2 -= s2 >= A::NSLOT ? A::NSLOT : 0;
+            const unsigned om = (unsigned)(s1 * A::SLOT_BYTES) + corner, o0 = (unsigned)(s2 * A::SLOT_BYTES) + corner;
+            const unsigned Um = su_a + om, U0 = su_a + o0, Vm = sv_a + om, V0 = sv_a + o0, Wm = sw_a + om, W0 = sw_a + o0;
+            const Window win{bx0, by0, max(z - A::HALO, zv.x), min(z + A::HALO, zv.y), z - A::HALO, sb};
+            // 8-point face sums in the reference's order (avgU/avgV/avgW cu:409-447), then *0.125
+            float au = 0.f, av = 0.f, aw = 0.f;
+            if (doV || doW) { // u at (x, y), (x+1, y), (x, y-1), (x+1, y-1) of planes z-1, z
+                float a = lds32<C00>(Um);
+                a = __fadd_rn(a, lds32<C00 + 4>(Um)); a = __fadd_rn(a, lds32<4>(Um)); a = __fadd_rn(a, lds32<8>(Um));
+                a = __fadd_rn(a, lds32<C00>(U0)); a = __fadd_rn(a, lds32<C00 + 4>(U0)); a = __fadd_rn(a, lds32<4>(U0));
+                a = __fadd_rn(a, lds32<8>(U0));
+                au = __fmul_rn(a, 0.125f);
+            }
+            if (doU || doW) { // v at (x, y), (x-1, y), (x, y+1), (x-1, y+1) of planes z-1, z
+                float a = lds32<C00>(Vm);
+                a = __fadd_rn(a, lds32<C00 - 4>(Vm)); a = __fadd_rn(a, lds32<C00 + BX4>(Vm)); a = __fadd_rn(a, lds32<C00 + BX4 - 4>(Vm));
+                a = __fadd_rn(a, lds32<C00>(V0)); a = __fadd_rn(a, lds32<C00 - 4>(V0)); a = __fadd_rn(a, lds32<C00 + BX4>(V0));
+                a = __fadd_rn(a, lds32<C00 + BX4 - 4>(V0));
+                av = __fmul_rn(a, 0.125f);
+            }
+            if (doU || doV) { // w at (x, y), (x-1, y), (x, y-1), (x-1, y-1) of planes z, z-1
+                float a = lds32<C00>(W0);
+                a = __fadd_rn(a, lds32<C00 - 4>(W0)); a = __fadd_rn(a, lds32<4>(W0)); a = __fadd_rn(a, lds32<0>(W0));
+                a = __fadd_rn(a, lds32<C00>(Wm)); a = __fadd_rn(a, lds32<C00 - 4>(Wm)); a = __fadd_rn(a, lds32<4>(Wm));
+                a = __fadd_rn(a, lds32<0>(Wm));
+                aw = __fmul_rn(a, 0.125f);
+            }
+            const float zh = __fadd_rn((float)z, 0.5f); // = half_up(z): exact below 2^23
+            if (doU) {
+                const float px = __fmaf_rn(-lds32<C00>(U0), dt, xf);
+                const float py = __fmaf_rn(-av, dt, yh);
+                const float pz = __fmaf_rn(-aw, dt, zh);
+                u1[n] = sample_staged(win, su_a, u0, P, S, g.zlo, px, py, pz, 0.f, .5f, .5f, bx, by, bz, zv, flag);
+            }
+            if (doV) {
+                const float px = __fmaf_rn(-au, dt, xh);
+                const float py = __fmaf_rn(-lds32<C00>(V0), dt, yf);
+                const float pz = __fmaf_rn(-aw, dt, zh);
+                v1[n] = sample_staged(win, sv_a, v0, P, S, g.zlo, px, py, pz, .5f, 0.f, .5f, bx, by, bz, zv, flag);
+            }
+            if (doW) {
+                const float px = __fmaf_rn(-au, dt, xh);
+                const float py = __fmaf_rn(-av, dt, yh);
+                const float pz = __fmaf_rn(-lds32<C00>(W0), dt, (float)z);
+                w1[n] = sample_staged(win, sw_a, w0, P, S, g.zlo, px, py, pz, .5f, .5f, 0.f, bx, by, bz, zv, flag);
             }
         }
+        n += g.nplane;
+        __syncthreads(); // every thread is done with step z: the free slot (the one in front of sb) takes plane z+HALO+1
+        if (tid == 0 && z + 1 < z_last) issue(z + A::HALO + 1, sb == 0 ? A::NSLOT - 1 : sb - 1);
         sb = sb + 1 == A::NSLOT ? 0 : sb + 1;
-        __syncthreads(); // plane z-HALO is no longer read: its slot may take plane z+HALO+1
-        if (tid == 0 && z + 1 < z_last) issue(z + A::HALO + 1);
+        if (++ws == A::NSLOT) { ws = 0; wpar ^= 1u; }
     }
 }
 
