@@ -16,6 +16,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <queue>
 #include <string>
 #include <vector>
 
@@ -423,15 +425,21 @@ int pick_zchunk_tma(smk_sim* s, int tx, int ty, int K, int nzn)
     const int sms = std::max(1, s->num_sms);
     int best_n = 1;
     double best = 1e300;
-    std::vector<double> busy;
-    for (int n = 1; n <= std::max(1, nzn / (2 * K)); n++) {
+    // chunk counts worth looking at: at least 2K planes per chunk, and no more pieces than ~64 per SM (beyond that the
+    // lead-in planes dominate anyway) -- keeps the search at a few hundred thousand heap operations even at 1024^3
+    const int n_max = std::max(1, std::min(nzn / (2 * K), (64 * sms) / std::max(1, tx * ty) + 1));
+    for (int n = 1; n <= n_max; n++) {
         const int zc = (nzn + n - 1) / n;
         const int nch = (nzn + zc - 1) / zc;
         if (nch != n) continue;
-        busy.assign((size_t)sms, 0.0);
-        auto put = [&](double cost) { // (a heap would do; the lists are a few hundred entries)
-            auto it = std::min_element(busy.begin(), busy.end());
-            *it += cost;
+        std::priority_queue<double, std::vector<double>, std::greater<double>> busy; // time at which each SM frees up
+        for (int i = 0; i < sms; i++) busy.push(0.0);
+        double span = 0.0;
+        auto put = [&](double cost) { // the next CTA of the grid goes to the first SM that frees up
+            const double t = busy.top() + cost;
+            busy.pop();
+            busy.push(t);
+            span = std::max(span, t);
         };
         const double setup = 1.5; // prologue + pipeline fill of a piece, in z-steps
         for (int pass = 0; pass < 2; pass++)
@@ -441,7 +449,6 @@ int pick_zchunk_tma(smk_sim* s, int tx, int ty, int K, int nzn)
                 if (pass == 0) for (int i = 0; i < tx; i++) put(1.45 * steps);
                 else for (int i = 0; i < tx * (ty - 1); i++) put(steps);
             }
-        const double span = *std::max_element(busy.begin(), busy.end());
         if (span < best - 1e-9) { best = span; best_n = n; }
     }
     s->zchunk_cache.push_back({tx, ty, K, nzn, (nzn + best_n - 1) / best_n});
