@@ -236,3 +236,23 @@ def test_omega_product_in_binary32_equals_the_double_product_for_every_input(smk
     bad, ties = smk.selfcheck_omega()
     assert bad == 0
     assert 190_000_000 < ties < 210_000_000        # 199 648 560 on the CPU twin
+
+
+def test_pass_kernel_choice_is_automatic_by_grid_size_and_identical_either_way(po, smk):
+    """smk_set_pass_kernel(AUTO): the TMA-staged pass from 5 M nodes per slab, the round-1 kernel below (launch-bound grids);
+    forcing either kernel on the same scene gives the same bits (device hashes of every field)."""
+    small = smk.SmokeSim(64, 64, 64); po.setup_scene(small, (64, 64, 64, -9.82, 4.0, [(32, 12, 32, 5)], []))
+    small.set_pass_kernel("auto"); small.step(0.01)
+    assert small.last_pass_kernel() == "reg"
+    small.close()
+    n = 176   # 177^3 = 5.5 M nodes
+    scene = (n, n, n, -9.82, 6.0, [(n / 2, n / 6, n / 2, n / 12)], [(n / 2, n / 2, n / 2, n / 10)])
+    hashes = {}
+    for kind in ("auto", "reg", "tma"):
+        s = smk.SmokeSim(n, n, n); po.setup_scene(s, scene); s.set_pass_kernel(kind)
+        for t in range(2):
+            s.step(po.tick_dt(t))
+        hashes[kind] = (s.last_pass_kernel(), s.hash_owned())
+        s.close()
+    assert hashes["auto"][0] == "tma" and hashes["reg"][0] == "reg" and hashes["tma"][0] == "tma"
+    assert hashes["auto"][1] == hashes["reg"][1] == hashes["tma"][1]
