@@ -174,6 +174,10 @@ struct PassRange {
     PeerPlanes lower, upper;
     PeerPlanes local;    // this slab's own input set and density, as plane-0 bases like the neighbours'
     PassSync sync;
+    // z-chunks of unequal length (TMA-staged pass on one GPU): chunk c writes the planes [zcut[c], zcut[c+1]); nzcut = 0:
+    // equal chunks of `zchunk` planes.  Long chunks first, one short chunk last: it fills the tail of the last wave.
+    int nzcut;
+    int zcut[18];
 };
 
 __device__ __forceinline__ void force_clamp_node(float& u, float& v, float& w, unsigned cd, float d, bool clampable,

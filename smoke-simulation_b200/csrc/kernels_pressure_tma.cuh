@@ -714,8 +714,9 @@ k_pressure_tma(GridP g, const __grid_constant__ PassMaps maps, float* __restrict
             __syncthreads();
         }
     }
-    const int zo0 = pr.out_lo + chunk * zchunk; // output node planes [zo0, zo1)
-    const int zo1 = min(zo0 + zchunk, pr.out_hi);
+    int zo0 = pr.out_lo + chunk * zchunk; // output node planes [zo0, zo1)
+    int zo1 = min(zo0 + zchunk, pr.out_hi);
+    if (pr.nzcut > 0) { zo0 = pr.zcut[chunk]; zo1 = pr.zcut[chunk + 1]; }
     if (zo0 < zo1) {
         // Does any plane this piece loads hold a COMPLEX cell inside the tile (halo included)?  cflag[z][by][bx] is written
         // with the stencil codes (k_codes*, K = 4 tile geometry); without it the general update is always compiled in.

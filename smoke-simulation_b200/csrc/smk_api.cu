@@ -184,6 +184,7 @@ struct smk_sim {
     };
     std::vector<DevSchedule> schedules;
     std::vector<std::array<int, 5>> zchunk_cache; // pick_zchunk_tma: {tx, ty, K, planes, chunk}
+    std::vector<std::pair<std::array<int, 4>, std::vector<int>>> chunks_cache; // pick_chunks_tma: {tx, ty, K, planes} -> lengths
     std::vector<const void*> configured; // kernels whose dynamic shared-memory limit has been raised on this handle's device
     std::string err;
 };
@@ -453,6 +454,56 @@ int pick_zchunk_tma(smk_sim* s, int tx, int ty, int K, int nzn)
     }
     s->zchunk_cache.push_back({tx, ty, K, nzn, (nzn + best_n - 1) / best_n});
     return s->zchunk_cache.back()[4];
+}
+
+// The same simulation over chunk lists of UNEQUAL length (one GPU): nb long chunks of equal size first, one short chunk
+// last -- longest-processing-time-first at the granularity the L2 argument allows (all tiles of a chunk still march
+// together).  In the model this takes 9 % (256^3) / 5 % (512^3) off the span of the best equal split.  Returns the chunk
+// lengths in dispatch order (empty: keep the equal split); cached per shape like pick_zchunk_tma.
+std::vector<int> pick_chunks_tma(smk_sim* s, int tx, int ty, int K, int nzn)
+{
+    for (const auto& e : s->chunks_cache)
+        if (e.first[0] == tx && e.first[1] == ty && e.first[2] == K && e.first[3] == nzn) return e.second;
+    const int sms = std::max(1, s->num_sms);
+    auto span_of = [&](const std::vector<int>& chunks) {
+        std::priority_queue<double, std::vector<double>, std::greater<double>> busy;
+        for (int i = 0; i < sms; i++) busy.push(0.0);
+        double span = 0.0;
+        auto put = [&](double cost) {
+            const double t = busy.top() + cost;
+            busy.pop();
+            busy.push(t);
+            span = std::max(span, t);
+        };
+        for (int pass = 0; pass < 2; pass++)
+            for (int planes : chunks) {
+                const double steps = planes + 2 * K + 1.5;
+                if (pass == 0) for (int i = 0; i < tx; i++) put(1.45 * steps);
+                else for (int i = 0; i < tx * (ty - 1); i++) put(steps);
+            }
+        return span;
+    };
+    std::vector<int> best_chunks;
+    double best = 1e300;
+    const int nb_max = std::max(1, std::min(std::min(nzn / (2 * K), 16), (64 * sms) / std::max(1, tx * ty) + 1));
+    for (int nb = 1; nb <= nb_max; nb++) {
+        const int a_max = (nzn + nb - 1) / nb;
+        const int step = std::max(2, a_max / 32);
+        for (int small = 0; small <= a_max; small = small == 0 ? 2 * K : small + step) {
+            const int rest = nzn - small;
+            if (rest < nb * K) break;
+            std::vector<int> ch;
+            const int A = (rest + nb - 1) / nb;
+            for (int left = rest; left > 0; left -= A) ch.push_back(std::min(A, left));
+            if ((int)ch.size() != nb || ch.back() < K) continue;
+            if (small) ch.push_back(small);
+            if ((int)ch.size() > 17) continue;
+            const double sp = span_of(ch);
+            if (sp < best - 1e-9) { best = sp; best_chunks = ch; }
+        }
+    }
+    s->chunks_cache.push_back({{tx, ty, K, nzn}, best_chunks});
+    return best_chunks;
 }
 
 int ensure_scratch(smk_sim*) { return SMK_OK; } // the scratch set is part of the arena
@@ -796,7 +847,18 @@ int launch_reg_pass(smk_sim* s, int sweep0, int out_lo, int out_hi, bool from_pe
                 g, s->u[n], s->v[n], s->w[n], s->scratch[0], s->scratch[1], s->scratch[2], s->code, sweep0, pr, fa, ds->pieces,
                 ds->first);
         } else {
-            launch_k(dim3((unsigned)tx, (unsigned)ty, (unsigned)nchunks), s->stream, zchunk, pr);
+            static const bool equal_chunks = getenv("SMK_PASS_EQUAL_CHUNKS") != nullptr; // A/B switch
+            unsigned gz = (unsigned)nchunks;
+            if (use_tma && !from_peers && !equal_chunks && force_chunks <= 0) {
+                const std::vector<int> ch = pick_chunks_tma(s, tx, ty, K, nz);
+                if (ch.size() >= 2) {
+                    pr.nzcut = (int)ch.size();
+                    pr.zcut[0] = out_lo;
+                    for (size_t i = 0; i < ch.size(); i++) pr.zcut[i + 1] = pr.zcut[i] + ch[i];
+                    gz = (unsigned)ch.size();
+                }
+            }
+            launch_k(dim3((unsigned)tx, (unsigned)ty, gz), s->stream, zchunk, pr);
         }
     }
     swap_in_scratch(s);
