@@ -169,3 +169,25 @@ def test_union_obstacle_extension_is_the_or_of_single_obstacle_masks(po):
     want = np.minimum.reduce(singles)
     assert np.array_equal(mask_for(obs, 1), want)
     assert not np.array_equal(mask_for(obs, 0), want)  # the reference rule really differs on this scene
+
+
+def test_binary32_omega_product_host_twin_sampled(tmp_path):
+    """The CPU twin of the pressure pass's binary32 evaluation of `(float)((double)q * -1.9)` (cu:384;
+    tools/experiments/omega_fp32_exhaustive.c) on every 251st bit pattern -- the full 2^32 sweep takes a minute on 8 cores and
+    runs on the device in the GPU suite (smk_selfcheck_omega).  Exit status 0 = no input in the valid range differs from
+    the double-precision product; the tie-to-even rule must fire on 1/19 of the inputs, and the constants printed are the ones
+    the kernel uses."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "omega_check")
+    subprocess.run(["/usr/bin/gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-o", exe,
+                    os.path.join(root, "tools", "experiments", "omega_fp32_exhaustive.c"), "-lm"], check=True)
+    r = subprocess.run([exe, "251"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    assert "different from the reference: 0 " in r.stdout
+    assert "0xbff33333" in r.stdout and "0xb2ccc8cd" in r.stdout and "0xb2ccd0cd" in r.stdout
+    kernel = open(os.path.join(root, "smoke-simulation_b200", "csrc", "kernels_pressure_tma.cuh")).read()
+    for c in ("-0x1.e66666p+0f", "-0x1.99919ap-26f", "-0x1.99a19ap-26f"):
+        assert c in kernel
+    ties = float(r.stdout.split("ties broken to even): ")[1].split("= ")[1].split(" %")[0])
+    assert 4.5 < ties < 4.8

@@ -12,17 +12,19 @@
 // product rounds ONTO the midpoint and the conversion to binary32 breaks the tie to even.
 // Needs the small products free of underflow: the kernel sends 0 < |d| < 2^-96 (d = n q, n <= 6) to the F2F / DMUL / F2F path, so
 // here every |q| >= 2^-99 (and q = +-0, sign included) must match; smaller inputs are only counted.
-// Build / run:  gcc -O2 -march=native -fopenmp -ffp-contract=off -o /tmp/omega_check tools/experiments/omega_fp32_exhaustive.c -lm && /tmp/omega_check
+// Build / run:  gcc -O2 -march=native -fopenmp -ffp-contract=off -o /tmp/omega_check tools/experiments/omega_fp32_exhaustive.c -lm && /tmp/omega_check [stride]
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 
-int main(void)
+int main(int argc, char** argv)
 {
+    const long long stride = argc > 1 ? atoll(argv[1]) : 1; // 1 = every bit pattern (about a minute on 8 cores); tests sample
     const double c = -1.9;
     const float ch = (float)c, cl = (float)(c - (double)ch);
     const float eps = 0x1p-39f, clp = cl + eps, clm = cl - eps;
@@ -30,7 +32,7 @@ int main(void)
     printf("ch = %a (0x%08x)  cl = %a (0x%08x)  cl+eps = %a (0x%08x)  cl-eps = %a (0x%08x)\n", ch, f2u(ch), cl, f2u(cl), clp, f2u(clp), clm, f2u(clm));
     unsigned long long ties = 0, wrong = 0, wrong_small = 0, checked = 0, not_adjacent = 0;
 #pragma omp parallel for reduction(+ : ties, wrong, wrong_small, checked, not_adjacent) schedule(static)
-    for (long long i = 0; i < (1ll << 32); i++) {
+    for (long long i = 0; i < (1ll << 32); i += stride) {
         const uint32_t b = (uint32_t)i;
         if ((b & 0x7f800000u) == 0x7f800000u) continue; // inf / nan: never produced (clamped fields)
         const float q = u2f(b);
