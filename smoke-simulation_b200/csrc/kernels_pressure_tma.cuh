@@ -6,9 +6,9 @@
 // z-step of which ~180 were address arithmetic, source selection, predicates and register moves outside the sweeps and
 // ~30 per sweep phase were stencil-code handling and copies; profiles/r1_final_pressure_reg_ncu_full.txt):
 //
-//   * INPUT PLANES ARRIVE BY TMA.  One elected thread issues cp.async.bulk.tensor.3d loads of the tile's next u, v, w
-//     (and stencil-code, and -- first pass of a step -- density) plane into a shared staging ring, NS-1 planes ahead,
-//     completion on an mbarrier.  Lanes read their quad with LDS.128 at immediate offsets: no per-lane global address,
+//   * INPUT PLANES ARRIVE BY TMA.  One elected thread issues ONE cp.async.bulk.tensor.4d load (x, y, z, field) for the
+//     tile's next u, v, w plane (plus one for the stencil codes and -- first pass of a step -- the density) into a
+//     shared staging ring, NS-1 planes ahead, completion on an mbarrier.  Lanes read their quad with LDS.128 at immediate offsets: no per-lane global address,
 //     no prefetch registers (13 + pointers in round 1), no bounds predicates -- the TMA unit zero-fills everything
 //     outside the stored planes, which is exactly the "plane does not exist" convention of the sweeps.
 //     Planes beyond the slab's owned range come from the NEIGHBOUR GPU's memory through tensor maps over its
@@ -21,7 +21,15 @@
 //     fluid neighbours" is one LOP3 + one vote; the rare paths -- cells next to a solid, denormal-range quotients -- are
 //     out-of-line functions, so the hot path is straight-line code the compiler does not pad with copies;
 //   * the lead-in / trapezoid conditions of the K sweeps of a step collapse into one per-step sweep count;
-//   * output addresses are three running per-lane pointers.
+//   * the register ring is never shifted in pieces without COMPLEX cells (loop unrolled over the K+2 rotations); pieces
+//     with COMPLEX cells (the floor row of every scene) run one compact step body per colour parity and shift the ring by
+//     moves -- unrolled, their code (every tier inline) overflowed the instruction cache;
+//   * p = (float)((double)q * -1.9) is evaluated exactly in binary32 (p_from_q: two fused roundings that bracket the doubly
+//     rounded product + a tie-to-even select; all 2^32 inputs checked on CPU and GPU), the double-precision sequence
+//     remains for denormal-range divergences only;
+//   * pieces of the bottom tile row are dispatched first, and on one GPU the z-chunks have unequal lengths (long first, one
+//     short last) chosen by a simulation of the hardware's dispatch order (smk_api.cu, pick_chunks_tma).
+// Measurements, the experiments that did not work and the instruction budget of a z-step: profiles/r2_tma_pass_final.txt.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -31,9 +39,6 @@
 #include "kernels_pressure_reg.cuh"
 #include "kernels_advect_tma.cuh" // mbarrier / TMA helpers
 
-#ifndef TINY_INL
-#define TINY_INL __noinline__
-#endif
 #ifndef GEN_INL
 #define GEN_INL __forceinline__
 #endif
